@@ -1,0 +1,156 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/vireo_b200.h declares,
+its scalar math agrees with scipy, and the product path refuses to run without a GPU (no CPU fallback).
+No compute entry point is called here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+from scipy.special import betaln, binom, digamma
+
+from conftest import ROOT
+from vireo_b200 import _lib
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "vireo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 13, names
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in names:
+        assert hasattr(raw, name), "libvireo_b200.so lacks %s" % name
+        assert name in _lib.SIGNATURES, "ctypes binding lacks %s" % name
+    assert lib.vb_version().decode().endswith("sm_100a")
+
+
+def test_struct_layouts_match_header():
+    # field order/size as in the header: 14 int32 + 1 double + 20 pointers; 8 int32 + 1 double + 16 pointers
+    assert ctypes.sizeof(_lib.VireoArgs) == 14 * 4 + 8 + 20 * 8
+    assert ctypes.sizeof(_lib.BmmArgs) == 8 * 4 + 8 + 16 * 8
+    assert ctypes.sizeof(_lib.WsSizes) == 7 * 8
+
+
+def test_library_is_built_for_sm100a():
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_device_digamma_formula_matches_scipy():
+    lib = _lib.load()
+    xs = np.concatenate([np.logspace(-6, 9, 400), [0.5, 1.0, 1.4616321449683623, 2.0, 9.999, 10.0, 49.5, 25.0]])
+    for x in xs:
+        got, want = lib.vb_host_digamma(float(x)), float(digamma(x))
+        assert abs(got - want) <= 2e-15 * max(1.0, abs(want)), (x, got, want)
+    assert np.isnan(lib.vb_host_digamma(0.0)) and np.isnan(lib.vb_host_digamma(-1.0))
+
+
+def test_device_beta_kl_matches_reference_formula():
+    lib = _lib.load()
+
+    def ref(p1, p2, q1, q2):   # vireoSNP/utils/vireo_base.py:96-127
+        def cross(a1, a2, b1, b2):
+            return betaln(b1, b2) - (b1 - 1) * digamma(a1) - (b2 - 1) * digamma(a2) + (b1 + b2 - 2) * digamma(a1 + a2)
+        return cross(p1, p2, q1, q2) - cross(p1, p2, p1, p2)
+
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        p1, p2 = np.exp(rng.uniform(-1, 12, 2))
+        q1, q2 = rng.choice([0.5, 1.0, 25.0, 49.5]), rng.choice([0.5, 1.0, 25.0, 49.5])
+        got, want = lib.vb_host_beta_kl(p1, p2, q1, q2), ref(p1, p2, q1, q2)
+        assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (p1, p2, q1, q2, got, want)
+
+
+def test_device_binom_term_matches_get_binom_coeff():
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    d = np.concatenate([rng.integers(1, 60, 300), rng.integers(60, 5000, 100), [1, 1, 2, 900, 1200, 85197]])
+    a = (d * rng.random(d.size)).astype(np.int64)
+    with np.errstate(over="ignore", divide="ignore"):
+        want = np.log(binom(d, a))
+    want[want > 700] = 700
+    want = want.astype(np.float32)
+    for ai, di, w in zip(a, d, want):
+        got = lib.vb_host_binom_term(int(ai), int(di))
+        assert got == w or abs(got - w) <= 1.2e-7 * abs(w), (ai, di, got, w)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import vireo_b200
+    m = vireo_b200.Vireo(n_cell=5, n_var=4, n_donor=2)
+    with pytest.raises(vireo_b200.VireoB200Error):
+        m.fit(np.ones((4, 5)), np.ones((4, 5)))
+    with pytest.raises(vireo_b200.VireoB200Error):
+        vireo_b200.BinomMixtureVB(n_cell=5, n_var=4, n_donor=2).fit(np.ones((4, 5)), np.ones((4, 5)))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "vireo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), "%s mentions the oracle" % f
+
+
+def test_api_surface_mirrors_reference():
+    """Names and signatures a vireoSNP user relies on (reference vireoSNP/__init__.py:12-15, doc/API.rst:59-75)."""
+    import inspect
+    import vireo_b200 as vb
+    assert vb.vireo_flock is vb.vireo_wrap
+    sig = inspect.signature(vb.Vireo.__init__)
+    assert list(sig.parameters)[1:] == ["n_cell", "n_var", "n_donor", "n_GT", "learn_GT", "learn_theta", "ASE_mode",
+                                        "fix_beta_sum", "beta_mu_init", "beta_sum_init", "ID_prob_init", "GT_prob_init"]
+    sig = inspect.signature(vb.Vireo.fit)
+    assert list(sig.parameters)[1:] == ["AD", "DP", "max_iter", "min_iter", "epsilon_conv", "delay_fit_theta",
+                                        "verbose", "n_inits", "nproc"]
+    assert sig.parameters["max_iter"].default == 200 and sig.parameters["min_iter"].default == 5
+    sig = inspect.signature(vb.vireo_wrap)
+    assert list(sig.parameters) == ["AD", "DP", "GT_prior", "n_donor", "learn_GT", "n_init", "random_seed",
+                                    "check_doublet", "max_iter_init", "delay_fit_theta", "n_extra_donor",
+                                    "extra_donor_mode", "check_ambient", "nproc", "kwargs"]
+    assert sig.parameters["n_init"].default == 20 and sig.parameters["nproc"].default == 4
+    sig = inspect.signature(vb.BinomMixtureVB.fit)
+    assert list(sig.parameters)[1:] == ["AD", "DP", "n_init", "max_iter", "max_iter_pre", "random_seed", "kwargs"]
+    for name in ("update_theta_size", "update_ID_prob", "update_GT_prob", "get_ELBO", "_fit_VB", "set_initial",
+                 "set_prior", "theta_s1", "theta_s2", "digamma1_", "digamma2_", "digammas_"):
+        assert hasattr(vb.Vireo, name), name
+
+
+def test_host_state_setup_matches_reference_semantics():
+    """Constructor RNG order (Q4) and the in-place GT_prior clipping (Q5) -- pure host logic."""
+    import vireo_b200 as vb
+    from oracle import vireo_oracle as O
+    np.random.seed(3)
+    m = vb.Vireo(n_cell=7, n_var=5, n_donor=3)
+    np.random.seed(3)
+    o = O.vireo_new(7, 5, 3)
+    assert np.array_equal(m.ID_prob, o.ID_prob) and np.array_equal(m.GT_prob, o.GT_prob)
+    assert np.array_equal(m.theta_s1_prior, o.theta_s1_prior) and np.array_equal(m.ID_prior, o.ID_prior)
+    prior = np.zeros((5, 3, 3)); prior[:, :, 0] = 1.0
+    keep = prior.copy()
+    m.set_prior(GT_prior=prior)
+    assert prior.min() == 1e-5 and prior.max() == 1 - 1e-5      # caller's array was clipped in place
+    o2 = O.vireo_new(7, 5, 3, ID_prob_init=m.ID_prob, GT_prob_init=m.GT_prob)
+    O.vireo_set_prior(o2, GT_prior=keep)
+    assert np.array_equal(m.GT_prior, o2.GT_prior)
+    np.random.seed(5)
+    b = vb.BinomMixtureVB(n_cell=6, n_var=4, n_donor=2)
+    np.random.seed(5)
+    ob = O.bmm_new(6, 4, 2)
+    assert np.array_equal(b.ID_prob, ob.ID_prob) and np.array_equal(b.beta_sum, ob.beta_sum)
+    assert np.array_equal(b.theta_s1_prior, ob.theta_s1_prior)

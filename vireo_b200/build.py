@@ -1,0 +1,49 @@
+"""Build libvireo_b200.so in-tree with nvcc for sm_100a.
+
+    python -m vireo_b200.build [--force] [--verbose]
+
+The shared library lands next to this file (vireo_b200/libvireo_b200.so) so that it travels to the
+GPU box with the repository snapshot; it is git-ignored.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(HERE, "csrc", f) for f in ("vb_stage.cu", "vb_em.cu")]
+DEPS = SRC + [os.path.join(HERE, "csrc", "vb_common.cuh"),
+              os.path.join(os.path.dirname(HERE), "include", "vireo_b200.h")]
+LIB = os.path.join(HERE, "libvireo_b200.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libvireo_b200.so cannot be built")
+
+
+def up_to_date():
+    if not os.path.exists(LIB):
+        return False
+    t = os.path.getmtime(LIB)
+    return all(os.path.getmtime(d) <= t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return LIB
+    cmd = [nvcc_path(), "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", "-shared",
+           "-Xptxas", "-v" if verbose else "-O3", "-o", LIB, *SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed (exit %d):\n%s" % (res.returncode, res.stderr[-4000:]))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,953 @@
+// vb_em.cu -- the variational-EM iteration of vireoSNP as sm_100a kernels (FP64, no tensor cores:
+// this is a sparse, bandwidth-bound reduction).
+//
+// One EM iteration of Vireo._fit_VB (vireoSNP/utils/vireo_model.py:257-264) is five launches:
+//   k_snp    SNP-major pass over the nnz:  S1 = AD @ R, S2 = (DP-AD) @ R        (:168-170, :207-209)
+//            + partial sums of S1*GT_old, S2*GT_old for the theta update          (:175-181)
+//   k_theta  reduce those sums, new Beta posterior (beta_mu, beta_sum)            (:183-185),
+//            digamma differences A_g = psi(s1)-psi(s1+s2), B_g = psi(s2)-psi(s1+s2) (:149-162), KL_theta
+//   k_gt     GT_prob = softmax_g(S1*A_g + S2*B_g + log GT_prior)                  (:211-219), KL_GT,
+//            and the per-(SNP, donor) tables  Wa = sum_g GT*A_g,  Wb = sum_g GT*B_g
+//   k_cell   cell-major pass over the nnz: logLik_ID = sum_i ad*Wa + (dp-ad)*Wb  (:190-196; the
+//            reference's 3 sparse products per genotype collapse into this one pass),
+//            ID_prob = softmax_k(logLik_ID + log ID_prior)                        (:198-199),
+//            partial sums of logLik_ID*ID_prob and KL(ID_prob || ID_prior)        (:236-237)
+//   k_elbo   ELBO = LB_p - KL_ID - KL_GT - KL_theta (:236-248) and the convergence rule (:266-274)
+// BinomMixtureVB._fit_BV (vireoSNP/utils/bmm_model.py:183-199) reuses k_snp / k_cell / k_elbo with
+// k_bmm_theta in place of k_theta + k_gt.
+//
+// All reductions are two-stage with a fixed launch geometry, so results are run-to-run identical.
+#include <string.h>
+
+#include <vector>
+
+#include "vb_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// launch accounting: every kernel launch of the EM path goes through VB_LAUNCH, which counts it and,
+// when profiling is enabled, brackets it with CUDA events on the launching stream.
+// classes: 0 k_snp, 1 k_theta, 2 k_gt, 3 k_cell, 4 k_elbo, 5 k_bmm_theta, 6 k_terms, 7 doublet helpers
+// ---------------------------------------------------------------------------------------------
+struct ProfEvent { int cls; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfEvent> g_prof_events;
+static int64_t g_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+#define VB_LAUNCH(cls, st, ...)                                         \
+    do {                                                                \
+        cudaEvent_t e0__ = nullptr, e1__ = nullptr;                     \
+        if (g_prof_on) {                                                \
+            cudaEventCreate(&e0__);                                     \
+            cudaEventCreate(&e1__);                                     \
+            cudaEventRecord(e0__, st);                                  \
+        }                                                               \
+        __VA_ARGS__;                                                    \
+        if (g_prof_on) {                                                \
+            cudaEventRecord(e1__, st);                                  \
+            g_prof_events.push_back(ProfEvent{cls, e0__, e1__});        \
+        }                                                               \
+        g_launches[cls] += 1;                                           \
+    } while (0)
+
+extern "C" void vb_profile_enable(int on) { g_prof_on = on != 0; }
+
+extern "C" int vb_profile_read(double* ms8, int64_t* n8) {
+    for (int i = 0; i < 8; ++i) { if (ms8) ms8[i] = 0.0; if (n8) n8[i] = 0; }
+    for (auto& ev : g_prof_events) {
+        float ms = 0.f;
+        cudaEventSynchronize(ev.e1);
+        if (cudaEventElapsedTime(&ms, ev.e0, ev.e1) == cudaSuccess) {
+            if (ms8) ms8[ev.cls] += ms;
+            if (n8) n8[ev.cls] += 1;
+        }
+        cudaEventDestroy(ev.e0);
+        cudaEventDestroy(ev.e1);
+    }
+    g_prof_events.clear();
+    return VB_OK;
+}
+
+extern "C" void vb_launch_counts(int64_t* n8) { for (int i = 0; i < 8; ++i) n8[i] = g_launches[i]; }
+
+// ---------------------------------------------------------------------------------------------
+// count decoding
+// ---------------------------------------------------------------------------------------------
+template <bool WIDE>
+__device__ __forceinline__ void decode(uint32_t c, uint32_t d, int& a, int& b) {
+    if (WIDE) { a = (int)c; b = (int)d - a; }
+    else { a = (int)(c & 0xffffu); b = (int)(c >> 16) - a; }
+}
+
+__device__ __forceinline__ double axpy_count(int n, double w, double acc) {
+    // unit counts dominate real data (about 90% of DP entries are 1): skip the int->double conversion
+    return n == 1 ? acc + w : fma((double)n, w, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_cell: one warp per cell.  KT lanes span the donor axis (KR registers each when K > 32),
+// so 32/KT nnz are in flight per step; the two tables are gathered by SNP id (L2-resident).
+// mode 0: fused softmax, writes ID_prob + logLik_ID + ELBO partials
+// mode 1: logLik_ID only, ELBO partials from the existing ID_prob
+// FUSED = false: columns [k_off, k_off + KT*KR) of a wider table, logLik only (doublet pass)
+// ---------------------------------------------------------------------------------------------
+template <int KT, int KR, bool WIDE, bool FUSED>
+__global__ void __launch_bounds__(VB_THREADS)
+k_cell(const CountsView m, const EmP p, const int mode, const int k_off) {
+    const int b = blockIdx.y;
+    if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
+    constexpr int NPW = 32 / KT;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int sub = lane / KT, kl = lane % KT;
+    const int K = p.K;
+    const double* __restrict__ Wa = p.Wa + (size_t)b * p.V * K;
+    const double* __restrict__ Wb = p.Wb + (size_t)b * p.V * K;
+    double* __restrict__ R = p.R ? p.R + (size_t)b * p.C * K : nullptr;
+    double* __restrict__ LL = p.ll + (size_t)b * p.C * K;
+    double lbp = 0.0, klid = 0.0;
+
+    const int64_t nw = (int64_t)gridDim.x * VB_WARPS;
+    for (int64_t j = (int64_t)blockIdx.x * VB_WARPS + wib; j < p.C; j += nw) {
+        double acc[KR];
+#pragma unroll
+        for (int r = 0; r < KR; ++r) acc[r] = 0.0;
+        const int64_t p0 = m.cell_ptr[j], p1 = m.cell_ptr[j + 1];
+        for (int64_t base = p0; base < p1; base += 32) {
+            const int64_t q = base + lane;
+            int idx = 0;
+            uint32_t c = 0, d = 0;
+            if (q < p1) {
+                idx = __ldg(m.cell_idx + q);
+                c = __ldg(m.cell_cnt + q);
+                if (WIDE) d = __ldg(m.cell_dp + q);
+            }
+            const int n = (int)((p1 - base) < 32 ? (p1 - base) : 32);
+#pragma unroll 4
+            for (int s = 0; s < KT; ++s) {
+                if (s * NPW >= n) break;                       // warp-uniform
+                const int src = s * NPW + sub;
+                const int i = __shfl_sync(VB_FULL, idx, src);
+                const uint32_t cc = __shfl_sync(VB_FULL, c, src);
+                const uint32_t dd = WIDE ? __shfl_sync(VB_FULL, d, src) : 0u;
+                if (src < n) {
+                    int av, bv;
+                    decode<WIDE>(cc, dd, av, bv);
+                    const size_t row = (size_t)i * K + k_off + kl;
+#pragma unroll
+                    for (int r = 0; r < KR; ++r) {
+                        if (k_off + kl + r * KT < K) {
+                            if (bv) acc[r] = axpy_count(bv, __ldg(Wb + row + r * KT), acc[r]);
+                            if (av) acc[r] = axpy_count(av, __ldg(Wa + row + r * KT), acc[r]);
+                        }
+                    }
+                }
+            }
+        }
+        // fold the NPW partial sums of each column (xor butterfly: every lane ends with the same bits)
+#pragma unroll
+        for (int off = KT; off < 32; off <<= 1)
+#pragma unroll
+            for (int r = 0; r < KR; ++r) acc[r] += __shfl_xor_sync(VB_FULL, acc[r], off);
+
+        if (!FUSED) {
+            if (sub == 0)
+#pragma unroll
+                for (int r = 0; r < KR; ++r) {
+                    const int k = k_off + kl + r * KT;
+                    if (k < K) LL[(size_t)j * K + k] = acc[r];
+                }
+            continue;
+        }
+
+        const size_t prow = (size_t)(p.id_rows == 1 ? 0 : j) * K;
+        double pr[KR];
+        if (mode == 0) {
+            double lg[KR], mx = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < KR; ++r) {
+                const int k = kl + r * KT;
+                lg[r] = k < K ? acc[r] + p.lidp[prow + k] : -INFINITY;
+                mx = fmax(mx, lg[r]);
+            }
+#pragma unroll
+            for (int off = KT / 2; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(VB_FULL, mx, off));
+            double z = 0.0;
+#pragma unroll
+            for (int r = 0; r < KR; ++r) {
+                pr[r] = (kl + r * KT < K) ? exp(lg[r] - mx) : 0.0;
+                z += pr[r];
+            }
+#pragma unroll
+            for (int off = KT / 2; off > 0; off >>= 1) z += __shfl_xor_sync(VB_FULL, z, off);
+#pragma unroll
+            for (int r = 0; r < KR; ++r) pr[r] = pr[r] / z;
+        } else {
+#pragma unroll
+            for (int r = 0; r < KR; ++r) {
+                const int k = kl + r * KT;
+                pr[r] = k < K ? R[(size_t)j * K + k] : 0.0;
+            }
+        }
+        if (sub == 0) {
+#pragma unroll
+            for (int r = 0; r < KR; ++r) {
+                const int k = kl + r * KT;
+                if (k < K) {
+                    const size_t e = (size_t)j * K + k;
+                    LL[e] = acc[r];
+                    if (mode == 0) R[e] = pr[r];
+                    lbp += acc[r] * pr[r];
+                    if (pr[r] > 0.0) klid += pr[r] * (log(pr[r]) - p.lidp_kl[prow + k]);
+                }
+            }
+        }
+    }
+    if (!FUSED) return;
+    __shared__ double sh[VB_WARPS];
+    const double t0 = block_sum(lbp, sh);
+    const double t1 = block_sum(klid, sh);
+    if (threadIdx.x == 0) {
+        double* out = p.part + (size_t)b * p.part_stride + p.off_cell + 2 * blockIdx.x;
+        out[0] = t0;
+        out[1] = t1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_snp: one warp per SNP.  Gathers ID_prob rows by cell id; two accumulators per column.
+// theta_mode: 0 never, 1 always, 2 when learn_theta and the device iteration counter >= delay
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool theta_on(const EmP& p, int b, int theta_mode) {
+    if (theta_mode == 1) return true;
+    if (theta_mode == 2) return p.learn_theta && p.ctrl[b * VB_CTRL_N + 1] >= p.delay;
+    return false;
+}
+
+template <int KT, int KR, bool WIDE>
+__global__ void __launch_bounds__(VB_THREADS)
+k_snp(const CountsView m, const EmP p, const int theta_mode) {
+    const int b = blockIdx.y;
+    if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
+    const bool do_theta = !p.bmm && theta_on(p, b, theta_mode);
+    if (!p.bmm && !do_theta && !p.learn_gt && theta_mode == 2) return;   // nothing consumes S1/S2 this iteration
+    constexpr int NPW = 32 / KT;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int sub = lane / KT, kl = lane % KT;
+    const int K = p.K, G = p.G;
+    const double* __restrict__ R = p.R + (size_t)b * p.C * K;
+    const double* __restrict__ GT = p.GT ? p.GT + (size_t)b * p.V * K * G : nullptr;
+    double* __restrict__ S1 = p.S1 + (size_t)b * p.V * K;
+    double* __restrict__ S2 = p.S2 + (size_t)b * p.V * K;
+    double t1[VB_MAX_GT], t2[VB_MAX_GT];
+#pragma unroll
+    for (int g = 0; g < VB_MAX_GT; ++g) t1[g] = t2[g] = 0.0;
+
+    const int64_t nw = (int64_t)gridDim.x * VB_WARPS;
+    for (int64_t i = (int64_t)blockIdx.x * VB_WARPS + wib; i < p.V; i += nw) {
+        double a1[KR], a2[KR];
+#pragma unroll
+        for (int r = 0; r < KR; ++r) a1[r] = a2[r] = 0.0;
+        const int64_t p0 = m.snp_ptr[i], p1 = m.snp_ptr[i + 1];
+        for (int64_t base = p0; base < p1; base += 32) {
+            const int64_t q = base + lane;
+            int idx = 0;
+            uint32_t c = 0, d = 0;
+            if (q < p1) {
+                idx = __ldg(m.snp_idx + q);
+                c = __ldg(m.snp_cnt + q);
+                if (WIDE) d = __ldg(m.snp_dp + q);
+            }
+            const int n = (int)((p1 - base) < 32 ? (p1 - base) : 32);
+#pragma unroll 4
+            for (int s = 0; s < KT; ++s) {
+                if (s * NPW >= n) break;
+                const int src = s * NPW + sub;
+                const int j = __shfl_sync(VB_FULL, idx, src);
+                const uint32_t cc = __shfl_sync(VB_FULL, c, src);
+                const uint32_t dd = WIDE ? __shfl_sync(VB_FULL, d, src) : 0u;
+                if (src < n) {
+                    int av, bv;
+                    decode<WIDE>(cc, dd, av, bv);
+                    const size_t row = (size_t)j * K + kl;
+#pragma unroll
+                    for (int r = 0; r < KR; ++r) {
+                        if (kl + r * KT < K) {
+                            const double w = __ldg(R + row + r * KT);
+                            if (av) a1[r] = axpy_count(av, w, a1[r]);
+                            if (bv) a2[r] = axpy_count(bv, w, a2[r]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int off = KT; off < 32; off <<= 1)
+#pragma unroll
+            for (int r = 0; r < KR; ++r) {
+                a1[r] += __shfl_xor_sync(VB_FULL, a1[r], off);
+                a2[r] += __shfl_xor_sync(VB_FULL, a2[r], off);
+            }
+        if (sub == 0) {
+#pragma unroll
+            for (int r = 0; r < KR; ++r) {
+                const int k = kl + r * KT;
+                if (k < K) {
+                    const size_t e = (size_t)i * K + k;
+                    S1[e] = a1[r];
+                    S2[e] = a2[r];
+                    if (do_theta) {
+#pragma unroll
+                        for (int g = 0; g < VB_MAX_GT; ++g)
+                            if (g < G) {
+                                const double gt = GT[e * G + g];
+                                t1[g] += a1[r] * gt;
+                                t2[g] += a2[r] * gt;
+                            }
+                    }
+                }
+            }
+        }
+        if (do_theta && p.ase) {
+            // allele-specific mode: theta is per SNP (vireo_model.py:177 `axis=1`): finish this row now.
+            // The raw sums are parked in the `ab` rows that k_theta_ase overwrites afterwards.
+            double* row = p.ab + ((size_t)b * p.T + i) * 2 * G;
+#pragma unroll
+            for (int g = 0; g < VB_MAX_GT; ++g)
+                if (g < G) {
+                    const double u1 = warp_sum(t1[g]), u2 = warp_sum(t2[g]);
+                    if (lane == 0) { row[g] = u1; row[G + g] = u2; }
+                    t1[g] = t2[g] = 0.0;
+                }
+        }
+    }
+    if (!do_theta || p.ase) return;
+    __shared__ double sh[VB_WARPS][2 * VB_MAX_GT];
+#pragma unroll
+    for (int g = 0; g < VB_MAX_GT; ++g) {
+        if (g < G) {                                                  // G is grid-uniform
+            const double u1 = warp_sum(t1[g]), u2 = warp_sum(t2[g]);
+            if (lane == 0) { sh[wib][g] = u1; sh[wib][VB_MAX_GT + g] = u2; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * VB_MAX_GT) {
+        const int g = threadIdx.x % VB_MAX_GT;
+        double t = 0.0;
+        if (g < G)
+            for (int w = 0; w < VB_WARPS; ++w) t += sh[w][threadIdx.x];
+        p.part[(size_t)b * p.part_stride + p.off_theta + (size_t)blockIdx.x * 2 * VB_MAX_GT + threadIdx.x] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_theta (shared theta, T = 1): one CTA per restart
+// ---------------------------------------------------------------------------------------------
+struct ThetaOut { double A, B, kl; };
+
+__device__ __forceinline__ ThetaOut theta_finish(const EmP& p, bool do_theta, double sum1, double sum2, double q1,
+                                                 double q2, double* mu_io, double* sum_io) {
+    double mu = *mu_io, sm = *sum_io;
+    if (do_theta) {
+        const double s1 = q1 + sum1, s2 = q2 + sum2;          // vireo_model.py:173-181
+        mu = s1 / (s1 + s2);                                  // :183
+        if (!p.fix_beta_sum) sm = s1 + s2;                    // :184-185
+        *mu_io = mu;
+        *sum_io = sm;
+    }
+    const double e1 = mu * sm, e2 = (1.0 - mu) * sm;          // theta_s1 / theta_s2 (:139-147)
+    const double es = e1 + e2;
+    const double psi1 = vb_digamma(e1), psi2 = vb_digamma(e2), psis = vb_digamma(es);
+    ThetaOut o;
+    o.A = psi1 - psis;
+    o.B = psi2 - psis;
+    o.kl = vb_beta_kl(e1, e2, q1, q2, psi1, psi2, psis);
+    return o;
+}
+
+__global__ void __launch_bounds__(2 * VB_MAX_GT * 32) k_theta(const EmP p, const int theta_mode) {
+    const int b = blockIdx.y;
+    if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
+    const bool do_theta = theta_on(p, b, theta_mode);
+    const int G = p.G;
+    __shared__ double tot[2 * VB_MAX_GT];
+    __shared__ double kls[VB_MAX_GT];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;    // warp w sums slot w of every block partial
+    if (do_theta) {
+        const double* src = p.part + (size_t)b * p.part_stride + p.off_theta + w;
+        double t = 0.0;
+        for (int blk = lane; blk < p.n_snpblk; blk += 32) t += src[(size_t)blk * 2 * VB_MAX_GT];
+        t = warp_sum(t);
+        if (lane == 0) tot[w] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const int g = threadIdx.x;
+        ThetaOut o = theta_finish(p, do_theta, tot[g], tot[VB_MAX_GT + g], p.s1p[g], p.s2p[g],
+                                  p.mu + (size_t)b * G + g, p.sum + (size_t)b * G + g);
+        double* ab = p.ab + (size_t)b * 2 * G;
+        ab[g] = o.A;
+        ab[G + g] = o.B;
+        kls[g] = o.kl;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int g = 0; g < G; ++g) t += kls[g];
+        p.part[(size_t)b * p.part_stride + p.off_klth] = t;
+    }
+}
+
+// allele-specific mode: theta per SNP; raw sums arrive in the ab rows (see k_snp)
+__global__ void __launch_bounds__(VB_THREADS) k_theta_ase(const EmP p, const int theta_mode) {
+    const int b = blockIdx.y;
+    if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
+    const bool do_theta = theta_on(p, b, theta_mode);
+    const int G = p.G;
+    __shared__ double sh[VB_WARPS];
+    double kl = 0.0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < p.T; t += (int64_t)gridDim.x * blockDim.x) {
+        double* ab = p.ab + ((size_t)b * p.T + t) * 2 * G;
+        double r1[VB_MAX_GT], r2[VB_MAX_GT];
+#pragma unroll
+        for (int g = 0; g < VB_MAX_GT; ++g)
+            if (g < G) { r1[g] = do_theta ? ab[g] : 0.0; r2[g] = do_theta ? ab[G + g] : 0.0; }
+#pragma unroll
+        for (int g = 0; g < VB_MAX_GT; ++g)
+            if (g < G) {
+                const size_t pi = (size_t)(p.thp_rows == 1 ? 0 : t) * G + g;
+                ThetaOut o = theta_finish(p, do_theta, r1[g], r2[g], p.s1p[pi], p.s2p[pi],
+                                          p.mu + ((size_t)b * p.T + t) * G + g, p.sum + ((size_t)b * p.T + t) * G + g);
+                ab[g] = o.A;
+                ab[G + g] = o.B;
+                kl += o.kl;
+            }
+    }
+    const double t = block_sum(kl, sh);
+    if (threadIdx.x == 0) p.part[(size_t)b * p.part_stride + p.off_klth + blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_gt: one thread per (SNP, donor)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VB_THREADS) k_gt(const EmP p, const int do_gt) {
+    const int b = blockIdx.y;
+    if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
+    const int K = p.K, G = p.G;
+    const int64_t VK = p.V * K;
+    double* __restrict__ GT = p.GT + (size_t)b * VK * G;
+    const double* __restrict__ S1 = p.S1 + (size_t)b * VK;
+    const double* __restrict__ S2 = p.S2 + (size_t)b * VK;
+    double* __restrict__ Wa = p.Wa + (size_t)b * VK;
+    double* __restrict__ Wb = p.Wb + (size_t)b * VK;
+    __shared__ double sh[VB_WARPS];
+    double kl = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < VK; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / K;
+        const double* ab = p.ab + ((size_t)b * p.T + (p.ase ? i : 0)) * 2 * G;
+        double pr[VB_MAX_GT];
+        if (do_gt) {
+            const double s1 = S1[e], s2 = S2[e];
+            double mx = -INFINITY;
+#pragma unroll
+            for (int g = 0; g < VB_MAX_GT; ++g)
+                if (g < G) {
+                    pr[g] = s1 * ab[g] + s2 * ab[G + g] + p.lgtp[(size_t)e * G + g];
+                    mx = fmax(mx, pr[g]);
+                }
+            double z = 0.0;
+#pragma unroll
+            for (int g = 0; g < VB_MAX_GT; ++g)
+                if (g < G) { pr[g] = exp(pr[g] - mx); z += pr[g]; }
+#pragma unroll
+            for (int g = 0; g < VB_MAX_GT; ++g)
+                if (g < G) { pr[g] = pr[g] / z; GT[(size_t)e * G + g] = pr[g]; }
+        } else {
+#pragma unroll
+            for (int g = 0; g < VB_MAX_GT; ++g)
+                if (g < G) pr[g] = GT[(size_t)e * G + g];
+        }
+        double wa = 0.0, wb = 0.0;
+#pragma unroll
+        for (int g = 0; g < VB_MAX_GT; ++g)
+            if (g < G) {
+                wa += pr[g] * ab[g];
+                wb += pr[g] * ab[G + g];
+                if (pr[g] > 0.0) kl += pr[g] * (log(pr[g]) - p.lgtp_kl[(size_t)e * G + g]);
+            }
+        Wa[e] = wa;
+        Wb[e] = wb;
+    }
+    const double t = block_sum(kl, sh);
+    if (threadIdx.x == 0) p.part[(size_t)b * p.part_stride + p.off_klgt + blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_bmm_theta: BinomMixtureVB.update_theta_size (bmm_model.py:133-144) + the digamma tables of
+// get_E_logLik (:125-129) + KL_theta (:166-173); one thread per (variant, clone)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VB_THREADS) k_bmm_theta(const EmP p, const int do_theta) {
+    const int b = blockIdx.y;
+    if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
+    const int64_t VK = p.V * p.K;
+    __shared__ double sh[VB_WARPS];
+    double kl = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < VK; e += (int64_t)gridDim.x * blockDim.x) {
+        const size_t o = (size_t)b * VK + e;
+        ThetaOut t = theta_finish(p, do_theta != 0, do_theta ? p.S1[o] : 0.0, do_theta ? p.S2[o] : 0.0, p.s1p[e],
+                                  p.s2p[e], p.mu + o, p.sum + o);
+        p.Wa[o] = t.A;
+        p.Wb[o] = t.B;
+        kl += t.kl;
+    }
+    const double t = block_sum(kl, sh);
+    if (threadIdx.x == 0) p.part[(size_t)b * p.part_stride + p.off_klth + blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_terms: LB_p and KL_ID from a caller-supplied logLik_ID buffer (get_ELBO(logLik_ID), :236-237)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VB_THREADS) k_terms(const EmP p) {
+    const int b = blockIdx.y;
+    const int K = p.K;
+    const int64_t CK = p.C * K;
+    const double* __restrict__ R = p.R + (size_t)b * CK;
+    const double* __restrict__ LL = p.ll + (size_t)b * CK;
+    __shared__ double sh[VB_WARPS];
+    double lbp = 0.0, klid = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < CK; e += (int64_t)gridDim.x * blockDim.x) {
+        const double r = R[e];
+        lbp += LL[e] * r;
+        if (r > 0.0) klid += r * (log(r) - p.lidp_kl[p.id_rows == 1 ? (e % K) : e]);
+    }
+    const double t0 = block_sum(lbp, sh);
+    const double t1 = block_sum(klid, sh);
+    if (threadIdx.x == 0) {
+        double* out = p.part + (size_t)b * p.part_stride + p.off_cell + 2 * blockIdx.x;
+        out[0] = t0;
+        out[1] = t1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_elbo: final sums + the convergence rule.  advance = 1 inside the fit loop.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_elbo(const EmP p, const int advance) {
+    const int b = blockIdx.y;
+    int* ctrl = p.ctrl + b * VB_CTRL_N;
+    if (advance && ctrl[0]) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const double* part = p.part + (size_t)b * p.part_stride;
+    __shared__ double tot[4];
+    double t = 0.0;
+    if (w == 0) for (int i = lane; i < p.n_cellblk; i += 32) t += part[p.off_cell + 2 * i];
+    else if (w == 1) for (int i = lane; i < p.n_cellblk; i += 32) t += part[p.off_cell + 2 * i + 1];
+    else if (w == 2) { if (!p.bmm) for (int i = lane; i < p.n_elemblk; i += 32) t += part[p.off_klgt + i]; }
+    else for (int i = lane; i < p.n_klth; i += 32) t += part[p.off_klth + i];
+    t = warp_sum(t);
+    if (lane == 0) tot[w] = t;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const double E = tot[0] - tot[1] - tot[2] - tot[3];          // LB_p - KL_ID - KL_GT - KL_theta (:248)
+    double* sc = p.scal + (size_t)b * VB_SCAL_N;
+    sc[0] = E; sc[1] = tot[0]; sc[2] = tot[1]; sc[3] = tot[2]; sc[4] = tot[3];
+    if (!advance) return;
+    const int it = ctrl[1];
+    double* elbo = p.elbo + (size_t)b * p.max_iter;
+    elbo[it] = E;
+    bool brk = false;
+    if (it > p.min_iter) {                                       // strict, as the reference (:266)
+        const double prev = elbo[it - 1];
+        const bool dec = p.bmm ? (E - prev < -1e-6)              // bmm_model.py:191
+                               : (E < prev - 1e-6);              // vireo_model.py:267
+        if (dec) ctrl[3] += 1;                                   // reference only warns
+        else if (it == p.max_iter - 1) { /* "did not converge" warning, replayed on the host */ }
+        else if (E - prev < p.eps) brk = true;                   // :273
+    }
+    ctrl[2] = it;                                                // the reference returns ELBO[:it]
+    if (brk || it + 1 >= p.max_iter) ctrl[0] = 1;
+    else ctrl[1] = it + 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// doublet tables (vireo_doublet.py:85-136) and the doublet softmax (:64-68)
+// ---------------------------------------------------------------------------------------------
+
+// (a, b) of the idx-th pair in itertools.combinations(range(n), 2) order
+__device__ __forceinline__ void pair_of(int n, int idx, int& a, int& b) {
+    a = 0;
+    while (idx >= n - 1 - a) { idx -= n - 1 - a; ++a; }
+    b = a + 1 + idx;
+}
+
+// columns 0..K-1: singlets, genotype classes G..G2-1 carry zero mass; columns K..K2-1: donor pairs over
+// G2 = G + G(G-1)/2 classes.  theta for the mixed classes: mean of mu, geometric mean of sum.
+// ab2: [T, 2*G2] digamma differences for the G2 classes, precomputed by k_doublet_theta.
+__global__ void __launch_bounds__(64) k_doublet_theta(const double* __restrict__ mu, const double* __restrict__ sum,
+                                                      int64_t T, int G, double* __restrict__ ab2) {
+    const int G2 = G + G * (G - 1) / 2;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < T * G2; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = e / G2;
+        const int c = (int)(e % G2);
+        double m_, s_;
+        if (c < G) { m_ = mu[t * G + c]; s_ = sum[t * G + c]; }
+        else {
+            int g1, g2;
+            pair_of(G, c - G, g1, g2);
+            m_ = (mu[t * G + g1] + mu[t * G + g2]) / 2.0;       // vireo_doublet.py:98
+            s_ = sqrt(sum[t * G + g1] * sum[t * G + g2]);       // :99
+        }
+        const double e1 = s_ * m_, e2 = s_ * (1.0 - m_);        // :49-50
+        const double psis = vb_digamma(s_);                     // :51  digamma(beta_sum_both)
+        ab2[t * 2 * G2 + c] = vb_digamma(e1) - psis;
+        ab2[t * 2 * G2 + G2 + c] = vb_digamma(e2) - psis;
+    }
+}
+
+__global__ void __launch_bounds__(VB_THREADS) k_doublet_tables(const double* __restrict__ GT, const double* __restrict__ ab2,
+                                                               int64_t V, int K, int G, int ase,
+                                                               double* __restrict__ Wa, double* __restrict__ Wb) {
+    const int G2 = G + G * (G - 1) / 2;
+    const int K2 = K + K * (K - 1) / 2;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < V * K2; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / K2;
+        const int c = (int)(e % K2);
+        const double* ab = ab2 + (size_t)(ase ? i : 0) * 2 * G2;
+        const double* gi = GT + (size_t)i * K * G;
+        double wa = 0.0, wb = 0.0;
+        if (c < K) {
+            for (int g = 0; g < G; ++g) { const double pg = gi[c * G + g]; wa += pg * ab[g]; wb += pg * ab[G2 + g]; }
+        } else {
+            int k1, k2;
+            pair_of(K, c - K, k1, k2);
+            const double* A = gi + k1 * G;
+            const double* Bq = gi + k2 * G;
+            double pr[VB_MAX_GT + VB_MAX_GT * (VB_MAX_GT - 1) / 2];
+            double z = 0.0;
+            for (int g = 0; g < G; ++g) { pr[g] = A[g] * Bq[g]; z += pr[g]; }                 // :126-127
+            int cc = G;
+            for (int g1 = 0; g1 < G; ++g1)
+                for (int g2 = g1 + 1; g2 < G; ++g2) { pr[cc] = A[g1] * Bq[g2] + A[g2] * Bq[g1]; z += pr[cc]; ++cc; }   // :128-131
+            for (int g = 0; g < G2; ++g) { const double pg = pr[g] / z; wa += pg * ab[g]; wb += pg * ab[G2 + g]; }   // :133
+        }
+        Wa[e] = wa;
+        Wb[e] = wb;
+    }
+}
+
+// one warp per cell: LLR (:64-65) and softmax over all K2 columns with the doublet prior (:67-68)
+__global__ void __launch_bounds__(VB_THREADS) k_doublet_softmax(const double* __restrict__ LL, const double* __restrict__ lprior,
+                                                                int id_rows, int64_t C, int K, int K2,
+                                                                double* __restrict__ prob, double* __restrict__ llr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = (int64_t)gridDim.x * VB_WARPS;
+    for (int64_t j = (int64_t)blockIdx.x * VB_WARPS + (threadIdx.x >> 5); j < C; j += nw) {
+        const double* ll = LL + (size_t)j * K2;
+        const double* lp = lprior + (size_t)(id_rows == 1 ? 0 : j) * K2;
+        double ms = -INFINITY, md = -INFINITY, mx = -INFINITY;
+        for (int k = lane; k < K2; k += 32) {
+            const double v = ll[k];
+            if (k < K) ms = fmax(ms, v); else md = fmax(md, v);
+            mx = fmax(mx, v + lp[k]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            ms = fmax(ms, __shfl_xor_sync(VB_FULL, ms, off));
+            md = fmax(md, __shfl_xor_sync(VB_FULL, md, off));
+            mx = fmax(mx, __shfl_xor_sync(VB_FULL, mx, off));
+        }
+        double z = 0.0;
+        for (int k = lane; k < K2; k += 32) z += exp(ll[k] + lp[k] - mx);
+        z = warp_sum(z);
+        for (int k = lane; k < K2; k += 32) prob[(size_t)j * K2 + k] = exp(ll[k] + lp[k] - mx) / z;
+        if (lane == 0) llr[j] = md - ms;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: dispatch, iteration driver, C ABI
+// ---------------------------------------------------------------------------------------------
+static CountsView view_of(const vb_counts* m) {
+    CountsView v;
+    v.C = m->C; v.V = m->V; v.N = m->N;
+    v.cell_ptr = m->cell_ptr; v.cell_idx = m->cell_idx; v.cell_cnt = m->cell_cnt; v.cell_dp = m->cell_dp;
+    v.snp_ptr = m->snp_ptr; v.snp_idx = m->snp_idx; v.snp_cnt = m->snp_cnt; v.snp_dp = m->snp_dp;
+    return v;
+}
+
+// donor-axis tiling: KT lanes x KR registers >= K
+static bool tile_for(int K, int& KT, int& KR) {
+    if (K < 1 || K > VB_MAX_DONOR) return false;
+    KR = 1;
+    if (K <= 2) KT = 2; else if (K <= 4) KT = 4; else if (K <= 8) KT = 8; else if (K <= 16) KT = 16;
+    else { KT = 32; KR = (K + 31) / 32; }
+    return true;
+}
+
+#define VB_DISPATCH_TILE(KT_, KR_, WIDE_, ...)                                  \
+    do {                                                                          \
+        if (KT_ == 2) { constexpr int kt = 2, kr = 1; if (WIDE_) { constexpr bool wd = true; __VA_ARGS__; } else { constexpr bool wd = false; __VA_ARGS__; } } \
+        else if (KT_ == 4) { constexpr int kt = 4, kr = 1; if (WIDE_) { constexpr bool wd = true; __VA_ARGS__; } else { constexpr bool wd = false; __VA_ARGS__; } } \
+        else if (KT_ == 8) { constexpr int kt = 8, kr = 1; if (WIDE_) { constexpr bool wd = true; __VA_ARGS__; } else { constexpr bool wd = false; __VA_ARGS__; } } \
+        else if (KT_ == 16) { constexpr int kt = 16, kr = 1; if (WIDE_) { constexpr bool wd = true; __VA_ARGS__; } else { constexpr bool wd = false; __VA_ARGS__; } } \
+        else switch (KR_) {                                                       \
+            case 1: { constexpr int kt = 32, kr = 1; if (WIDE_) { constexpr bool wd = true; __VA_ARGS__; } else { constexpr bool wd = false; __VA_ARGS__; } } break; \
+            case 2: { constexpr int kt = 32, kr = 2; if (WIDE_) { constexpr bool wd = true; __VA_ARGS__; } else { constexpr bool wd = false; __VA_ARGS__; } } break; \
+            case 3: { constexpr int kt = 32, kr = 3; if (WIDE_) { constexpr bool wd = true; __VA_ARGS__; } else { constexpr bool wd = false; __VA_ARGS__; } } break; \
+            case 4: { constexpr int kt = 32, kr = 4; if (WIDE_) { constexpr bool wd = true; __VA_ARGS__; } else { constexpr bool wd = false; __VA_ARGS__; } } break; \
+            case 5: { constexpr int kt = 32, kr = 5; if (WIDE_) { constexpr bool wd = true; __VA_ARGS__; } else { constexpr bool wd = false; __VA_ARGS__; } } break; \
+            case 6: { constexpr int kt = 32, kr = 6; if (WIDE_) { constexpr bool wd = true; __VA_ARGS__; } else { constexpr bool wd = false; __VA_ARGS__; } } break; \
+            case 7: { constexpr int kt = 32, kr = 7; if (WIDE_) { constexpr bool wd = true; __VA_ARGS__; } else { constexpr bool wd = false; __VA_ARGS__; } } break; \
+            default: { constexpr int kt = 32, kr = 8; if (WIDE_) { constexpr bool wd = true; __VA_ARGS__; } else { constexpr bool wd = false; __VA_ARGS__; } } break; \
+        }                                                                         \
+    } while (0)
+
+static int launch_cell(const vb_counts* m, const EmP& p, int mode, cudaStream_t st) {
+    int KT, KR;
+    if (!tile_for(p.K, KT, KR)) { vb_set_error("n_donor=%d outside [1, %d]", p.K, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
+    const CountsView v = view_of(m);
+    const dim3 grid(m->grid_cell, p.B);
+    VB_LAUNCH(3, st, VB_DISPATCH_TILE(KT, KR, m->wide, k_cell<kt, kr, wd, true><<<grid, VB_THREADS, 0, st>>>(v, p, mode, 0)));
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
+static int launch_snp(const vb_counts* m, const EmP& p, int theta_mode, cudaStream_t st) {
+    int KT, KR;
+    if (!tile_for(p.K, KT, KR)) { vb_set_error("n_donor=%d outside [1, %d]", p.K, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
+    const CountsView v = view_of(m);
+    const dim3 grid(m->grid_snp, p.B);
+    VB_LAUNCH(0, st, VB_DISPATCH_TILE(KT, KR, m->wide, k_snp<kt, kr, wd><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode)));
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
+static void part_layout(const vb_counts* m, EmP& p) {
+    p.n_snpblk = m->grid_snp;
+    p.n_elemblk = m->grid_elem;
+    p.n_cellblk = m->grid_cell;
+    p.n_klth = (p.bmm || p.ase) ? m->grid_elem : 1;
+    p.off_theta = 0;
+    p.off_klgt = p.off_theta + p.n_snpblk * 2 * VB_MAX_GT;
+    p.off_cell = p.off_klgt + p.n_elemblk;
+    p.off_klth = p.off_cell + 2 * p.n_cellblk;
+    p.part_stride = p.off_klth + m->grid_elem;
+}
+
+static int fill_vireo(const vb_counts* m, const vb_vireo_args* a, EmP& p) {
+    if (!m || !a) { vb_set_error("NULL argument"); return VB_E_ARG; }
+    if (a->n_gt < 1 || a->n_gt > VB_MAX_GT) { vb_set_error("n_GT=%d outside [1, %d]", a->n_gt, VB_MAX_GT); return VB_E_UNSUPPORTED; }
+    if (a->n_donor < 1 || a->n_donor > VB_MAX_DONOR) { vb_set_error("n_donor=%d outside [1, %d]", a->n_donor, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
+    if (a->n_batch < 1 || a->n_batch > 65535) { vb_set_error("n_batch=%d outside [1, 65535]", a->n_batch); return VB_E_ARG; }
+    memset(&p, 0, sizeof(p));
+    p.C = m->C; p.V = m->V; p.T = a->ase_mode ? m->V : 1;
+    p.K = a->n_donor; p.G = a->n_gt; p.B = a->n_batch; p.bmm = 0;
+    p.ase = a->ase_mode; p.learn_gt = a->learn_gt; p.learn_theta = a->learn_theta; p.fix_beta_sum = a->fix_beta_sum;
+    p.id_rows = a->id_prior_rows; p.thp_rows = a->theta_prior_rows;
+    p.max_iter = a->max_iter; p.min_iter = a->min_iter; p.delay = a->delay_fit_theta; p.eps = a->epsilon_conv;
+    p.R = a->id_prob; p.GT = a->gt_prob; p.mu = a->beta_mu; p.sum = a->beta_sum;
+    p.lidp = a->log_id_prior; p.lidp_kl = a->log_id_prior_kl; p.lgtp = a->log_gt_prior; p.lgtp_kl = a->log_gt_prior_kl;
+    p.s1p = a->s1_prior; p.s2p = a->s2_prior;
+    p.S1 = a->S1; p.S2 = a->S2; p.Wa = a->Wa; p.Wb = a->Wb; p.ll = a->loglik; p.ab = a->ab; p.part = a->part;
+    p.scal = a->scal; p.elbo = a->elbo; p.ctrl = a->ctrl;
+    if (!p.R || !p.GT || !p.mu || !p.sum || !p.lidp || !p.lidp_kl || !p.lgtp || !p.lgtp_kl || !p.s1p || !p.s2p || !p.S1 ||
+        !p.S2 || !p.Wa || !p.Wb || !p.ll || !p.ab || !p.part || !p.scal || !p.ctrl) {
+        vb_set_error("NULL device pointer in vb_vireo_args");
+        return VB_E_ARG;
+    }
+    if ((p.id_rows != 1 && p.id_rows != m->C) || (p.thp_rows != 1 && p.thp_rows != p.T)) {
+        vb_set_error("prior rows must be 1 or the full extent");
+        return VB_E_ARG;
+    }
+    part_layout(m, p);
+    return VB_OK;
+}
+
+static int fill_bmm(const vb_counts* m, const vb_bmm_args* a, EmP& p) {
+    if (!m || !a) { vb_set_error("NULL argument"); return VB_E_ARG; }
+    if (a->n_donor < 1 || a->n_donor > VB_MAX_DONOR) { vb_set_error("n_donor=%d outside [1, %d]", a->n_donor, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
+    if (a->n_batch < 1 || a->n_batch > 65535) { vb_set_error("n_batch=%d outside [1, 65535]", a->n_batch); return VB_E_ARG; }
+    memset(&p, 0, sizeof(p));
+    p.C = m->C; p.V = m->V; p.T = m->V;
+    p.K = a->n_donor; p.G = 1; p.B = a->n_batch; p.bmm = 1;
+    p.fix_beta_sum = a->fix_beta_sum; p.learn_theta = 1;
+    p.id_rows = a->id_prior_rows; p.thp_rows = (int)m->V;
+    p.max_iter = a->max_iter; p.min_iter = a->min_iter; p.eps = a->epsilon_conv;
+    p.R = a->id_prob; p.mu = a->beta_mu; p.sum = a->beta_sum;
+    p.lidp = a->log_id_prior; p.lidp_kl = a->log_id_prior_kl; p.s1p = a->s1_prior; p.s2p = a->s2_prior;
+    p.S1 = a->S1; p.S2 = a->S2; p.Wa = a->Wa; p.Wb = a->Wb; p.ll = a->loglik; p.part = a->part;
+    p.scal = a->scal; p.elbo = a->elbo; p.ctrl = a->ctrl;
+    if (!p.R || !p.mu || !p.sum || !p.lidp || !p.lidp_kl || !p.s1p || !p.s2p || !p.S1 || !p.S2 || !p.Wa || !p.Wb ||
+        !p.ll || !p.part || !p.scal || !p.ctrl) {
+        vb_set_error("NULL device pointer in vb_bmm_args");
+        return VB_E_ARG;
+    }
+    if (p.id_rows != 1 && p.id_rows != m->C) { vb_set_error("id_prior_rows must be 1 or n_cell"); return VB_E_ARG; }
+    part_layout(m, p);
+    return VB_OK;
+}
+
+static int ws_sizes(const vb_counts* m, int K, int G, int B, int T_is_V, vb_ws_sizes* out) {
+    if (!m || !out || K < 1 || B < 1) { vb_set_error("bad argument"); return VB_E_ARG; }
+    EmP p;
+    memset(&p, 0, sizeof(p));
+    p.bmm = G == 0; p.ase = T_is_V;
+    part_layout(m, p);
+    const int64_t T = T_is_V ? m->V : 1;
+    out->S = (int64_t)B * m->V * K;
+    out->W = (int64_t)B * m->V * K;
+    out->loglik = (int64_t)B * m->C * K;
+    out->ab = (int64_t)B * T * 2 * (G ? G : 1);
+    out->part = (int64_t)B * p.part_stride;
+    out->scal = (int64_t)B * VB_SCAL_N;
+    out->ctrl = (int64_t)B * VB_CTRL_N;
+    return VB_OK;
+}
+
+extern "C" int vb_vireo_ws_sizes(const vb_counts* m, int n_donor, int n_gt, int n_batch, int ase_mode, vb_ws_sizes* out) {
+    if (n_gt < 1) { vb_set_error("n_GT must be >= 1"); return VB_E_ARG; }
+    return ws_sizes(m, n_donor, n_gt, n_batch, ase_mode, out);
+}
+extern "C" int vb_bmm_ws_sizes(const vb_counts* m, int n_donor, int n_batch, vb_ws_sizes* out) {
+    return ws_sizes(m, n_donor, 0, n_batch, 1, out);
+}
+
+// one Vireo iteration; theta_mode / gt flag as documented on the kernels
+static int vireo_iteration(const vb_counts* m, const EmP& p, int phases, bool in_loop, cudaStream_t st) {
+    int rc;
+    const dim3 one(1, p.B), elem(m->grid_elem, p.B);
+    const int theta_mode = in_loop ? 2 : ((phases & VB_PH_THETA) ? 1 : 0);
+    if (phases & VB_PH_SNP)
+        if ((rc = launch_snp(m, p, theta_mode, st))) return rc;
+    // k_theta always runs: the digamma tables and KL_theta depend on the current beta_mu / beta_sum
+    if (p.ase) VB_LAUNCH(1, st, k_theta_ase<<<elem, VB_THREADS, 0, st>>>(p, theta_mode));
+    else VB_LAUNCH(1, st, k_theta<<<one, 2 * VB_MAX_GT * 32, 0, st>>>(p, theta_mode));
+    VB_CUDA(cudaGetLastError());
+    const int do_gt = in_loop ? p.learn_gt : ((phases & VB_PH_GT) ? 1 : 0);
+    VB_LAUNCH(2, st, k_gt<<<elem, VB_THREADS, 0, st>>>(p, do_gt));
+    VB_CUDA(cudaGetLastError());
+    if (phases & VB_PH_ID) { if ((rc = launch_cell(m, p, 0, st))) return rc; }
+    else if (phases & VB_PH_LOGLIK) { if ((rc = launch_cell(m, p, 1, st))) return rc; }
+    else if (phases & VB_PH_ELBO) { VB_LAUNCH(6, st, k_terms<<<dim3(m->grid_cell, p.B), VB_THREADS, 0, st>>>(p)); VB_CUDA(cudaGetLastError()); }
+    if (phases & VB_PH_ELBO) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, in_loop ? 1 : 0)); VB_CUDA(cudaGetLastError()); }
+    return VB_OK;
+}
+
+static int bmm_iteration(const vb_counts* m, const EmP& p, int phases, bool in_loop, cudaStream_t st) {
+    int rc;
+    const dim3 one(1, p.B), elem(m->grid_elem, p.B);
+    if (phases & VB_PH_SNP)
+        if ((rc = launch_snp(m, p, 0, st))) return rc;
+    VB_LAUNCH(5, st, k_bmm_theta<<<elem, VB_THREADS, 0, st>>>(p, (in_loop || (phases & VB_PH_THETA)) ? 1 : 0));
+    VB_CUDA(cudaGetLastError());
+    if (phases & VB_PH_ID) { if ((rc = launch_cell(m, p, 0, st))) return rc; }
+    else if (phases & VB_PH_LOGLIK) { if ((rc = launch_cell(m, p, 1, st))) return rc; }
+    else if (phases & VB_PH_ELBO) { VB_LAUNCH(6, st, k_terms<<<dim3(m->grid_cell, p.B), VB_THREADS, 0, st>>>(p)); VB_CUDA(cudaGetLastError()); }
+    if (phases & VB_PH_ELBO) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, in_loop ? 1 : 0)); VB_CUDA(cudaGetLastError()); }
+    return VB_OK;
+}
+
+// pinned landing zone for the done flags
+static thread_local int32_t* g_pin = nullptr;
+static thread_local int g_pin_n = 0;
+
+static int run_loop(const vb_counts* m, const EmP& p, int poll_every, cudaStream_t st) {
+    if (p.max_iter < 1) { vb_set_error("max_iter must be >= 1"); return VB_E_ARG; }
+    if (!p.elbo) { vb_set_error("elbo output is NULL"); return VB_E_ARG; }
+    const int n_ctrl = p.B * VB_CTRL_N;
+    if (g_pin_n < n_ctrl) {
+        if (g_pin) cudaFreeHost(g_pin);
+        g_pin = nullptr; g_pin_n = 0;
+        VB_CUDA(cudaMallocHost(&g_pin, n_ctrl * sizeof(int32_t)));
+        g_pin_n = n_ctrl;
+    }
+    VB_CUDA(cudaMemsetAsync(p.ctrl, 0, n_ctrl * sizeof(int32_t), st));
+    if (poll_every <= 0) poll_every = 16;
+    const int all = VB_PH_SNP | VB_PH_THETA | VB_PH_GT | VB_PH_ID | VB_PH_ELBO;
+    for (int it = 0; it < p.max_iter; ++it) {
+        const int rc = p.bmm ? bmm_iteration(m, p, all, true, st) : vireo_iteration(m, p, all, true, st);
+        if (rc) return rc;
+        if ((it + 1) % poll_every == 0 && it + 1 < p.max_iter) {
+            VB_CUDA(cudaMemcpyAsync(g_pin, p.ctrl, n_ctrl * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaStreamSynchronize(st));
+            bool done = true;
+            for (int b = 0; b < p.B; ++b) done = done && g_pin[b * VB_CTRL_N];
+            if (done) break;
+        }
+    }
+    return VB_OK;
+}
+
+extern "C" int vb_vireo_fit(const vb_counts* m, const vb_vireo_args* a, void* stream) {
+    EmP p;
+    int rc = fill_vireo(m, a, p);
+    if (rc) return rc;
+    VB_CUDA(cudaSetDevice(m->device));
+    return run_loop(m, p, a->poll_every, (cudaStream_t)stream);
+}
+
+extern "C" int vb_vireo_step(const vb_counts* m, const vb_vireo_args* a, int phases, void* stream) {
+    EmP p;
+    int rc = fill_vireo(m, a, p);
+    if (rc) return rc;
+    VB_CUDA(cudaSetDevice(m->device));
+    p.ctrl = nullptr;                       // single phases never consult the loop state
+    return vireo_iteration(m, p, phases, false, (cudaStream_t)stream);
+}
+
+extern "C" int vb_bmm_fit(const vb_counts* m, const vb_bmm_args* a, void* stream) {
+    EmP p;
+    int rc = fill_bmm(m, a, p);
+    if (rc) return rc;
+    VB_CUDA(cudaSetDevice(m->device));
+    return run_loop(m, p, a->poll_every, (cudaStream_t)stream);
+}
+
+extern "C" int vb_bmm_step(const vb_counts* m, const vb_bmm_args* a, int phases, void* stream) {
+    EmP p;
+    int rc = fill_bmm(m, a, p);
+    if (rc) return rc;
+    VB_CUDA(cudaSetDevice(m->device));
+    p.ctrl = nullptr;
+    return bmm_iteration(m, p, phases, false, (cudaStream_t)stream);
+}
+
+extern "C" int vb_vireo_doublet(const vb_counts* m, int n_donor, int n_gt, int ase_mode,
+                                const double* gt_prob, const double* beta_mu, const double* beta_sum,
+                                const double* log_prior_both, int id_prior_rows,
+                                double* Wa, double* Wb, double* loglik_out, double* prob_out, double* llr_out,
+                                void* stream) {
+    if (!m || !gt_prob || !beta_mu || !beta_sum || !log_prior_both || !Wa || !Wb || !loglik_out || !prob_out || !llr_out) {
+        vb_set_error("NULL argument");
+        return VB_E_ARG;
+    }
+    if (n_gt < 1 || n_gt > VB_MAX_GT || n_donor < 1) { vb_set_error("unsupported n_GT=%d / n_donor=%d", n_gt, n_donor); return VB_E_UNSUPPORTED; }
+    VB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = n_donor, G = n_gt;
+    const int K2 = K + K * (K - 1) / 2, G2 = G + G * (G - 1) / 2;
+    const int64_t T = ase_mode ? m->V : 1;
+    double* ab2;
+    VB_CUDA(cudaMalloc(&ab2, (size_t)T * 2 * G2 * sizeof(double)));
+    struct Free { void* p; ~Free() { cudaFree(p); } } fr{ab2};
+    VB_LAUNCH(7, st, k_doublet_theta<<<(int)((T * G2 + 63) / 64 > 4096 ? 4096 : (T * G2 + 63) / 64), 64, 0, st>>>(beta_mu, beta_sum, T, G, ab2));
+    VB_CUDA(cudaGetLastError());
+    VB_LAUNCH(7, st, k_doublet_tables<<<m->grid_elem, VB_THREADS, 0, st>>>(gt_prob, ab2, m->V, K, G, ase_mode, Wa, Wb));
+    VB_CUDA(cudaGetLastError());
+    // cell-major pass over column chunks of the K2-wide tables
+    EmP p;
+    memset(&p, 0, sizeof(p));
+    p.C = m->C; p.V = m->V; p.K = K2; p.B = 1; p.Wa = Wa; p.Wb = Wb; p.ll = loglik_out; p.id_rows = 1;
+    const CountsView v = view_of(m);
+    const int chunk = K2 <= 16 ? (K2 <= 2 ? 2 : K2 <= 4 ? 4 : K2 <= 8 ? 8 : 16) : 128;
+    for (int k0 = 0; k0 < K2; k0 += chunk) {
+        const int width = K2 - k0 < chunk ? K2 - k0 : chunk;
+        int KT, KR;
+        tile_for(width, KT, KR);
+        const dim3 grid(m->grid_cell, 1);
+        VB_LAUNCH(3, st, VB_DISPATCH_TILE(KT, KR, m->wide, k_cell<kt, kr, wd, false><<<grid, VB_THREADS, 0, st>>>(v, p, 1, k0)));
+        VB_CUDA(cudaGetLastError());
+    }
+    VB_LAUNCH(7, st, k_doublet_softmax<<<m->grid_cell, VB_THREADS, 0, st>>>(loglik_out, log_prior_both, id_prior_rows, m->C, K, K2, prob_out, llr_out));
+    VB_CUDA(cudaGetLastError());
+    VB_CUDA(cudaStreamSynchronize(st));
+    return VB_OK;
+}
