@@ -97,9 +97,9 @@ def algorithmic_bytes(w, nnz, wide=False):
 # ------------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_throttle_reasons.hw_slowdown,"
+              "clocks_throttle_reasons.hw_thermal_slowdown,clocks_throttle_reasons.sw_thermal_slowdown,"
+              "clocks_throttle_reasons.sw_power_cap")
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, gpu_id):
@@ -108,7 +108,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_id), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -145,7 +145,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return None
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0,
+                    "error": " | ".join(l for _, l in self.rows[:2])[:300]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
                 "samples": len(sm)}
 
@@ -434,7 +435,10 @@ def run_b200(args):
             nz = ref_id > 1e-300
             parity = {"elbo_iter0_rel_diff": abs(chk[0]["ELBO"] - g_elbo) / abs(chk[0]["ELBO"]),
                       "id_prob_max_rel_diff": float(np.max(np.abs(g_id[nz] - ref_id[nz]) / ref_id[nz])),
-                      "argmax_equal": bool(np.array_equal(g_id.argmax(1), ref_id.argmax(1)))}
+                      # after ONE iteration from a random start most posteriors are near-uniform: report
+                      # argmax mismatches only where the top-2 gap is meaningful
+                      "argmax_mismatch_gap_gt_1e-9": int(np.sum((g_id.argmax(1) != ref_id.argmax(1)) &
+                                                                (np.diff(np.sort(ref_id, 1)[:, -2:], axis=1)[:, 0] > 1e-9)))}
 
     line = {
         "metric": "EM iterations/sec", "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps,

@@ -151,7 +151,10 @@ def _fingerprint(M):
         return ("dense", M.shape, M.ctypes.data, float(M.ravel()[:: max(1, M.size // 1024)].sum()))
     data = M.data
     step = max(1, data.size // 1024)
-    return (M.format, M.shape, int(M.nnz), data.ctypes.data, M.indices.ctypes.data,
+    index = getattr(M, "indices", None)
+    if index is None:
+        index = getattr(M, "row", data)
+    return (M.format, M.shape, int(M.nnz), data.ctypes.data, index.ctypes.data,
             float(data[::step].sum()) if data.size else 0.0)
 
 
@@ -192,6 +195,8 @@ def _dev(arr, device):
     """float64 C-contiguous host array -> device tensor."""
     t = torch()
     a = np.ascontiguousarray(arr, dtype=np.float64)
+    if not a.flags.writeable:
+        a = a.copy()
     return t.from_numpy(a).to("cuda:%d" % device)
 
 

@@ -103,7 +103,8 @@ class Vireo():
 
     # -- single updates (each is one or two kernel launches on the staged matrices) -----------------
     def _batch(self, AD, DP):
-        return _engine.VireoBatch(_engine.stage(AD, DP), [self])
+        self._last_counts = _engine.stage(AD, DP)
+        return _engine.VireoBatch(self._last_counts, [self])
 
     def update_theta_size(self, AD, DP):
         """theta posterior update (reference vireo_model.py:165-185): SNP-major pass + k_theta."""
