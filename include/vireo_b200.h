@@ -83,7 +83,7 @@ int vb_binom_const(const vb_counts* m, double* scratch, double* out_host, void* 
 /* Sizes of the per-call workspaces, in elements, for a batch of B restarts. */
 typedef struct vb_ws_sizes {
     int64_t S;        /* doubles: S1 and S2, each [B, n_var, K]                 */
-    int64_t W;        /* doubles: Wa and Wb, each [B, n_var, K]                 */
+    int64_t W;        /* doubles: per-allele tables [B, n_var, 2, K]           */
     int64_t loglik;   /* doubles: [B, n_cell, K]                               */
     int64_t ab;       /* doubles: [B, T, 2*G] digamma differences              */
     int64_t part;     /* doubles: block partial sums                           */
@@ -113,7 +113,7 @@ typedef struct vb_vireo_args {
     const double* s1_prior;         /* [theta_prior_rows, G]                                           */
     const double* s2_prior;
     /* workspace (see vb_vireo_ws_sizes) */
-    double *S1, *S2, *Wa, *Wb, *loglik, *ab, *part, *scal;
+    double *S1, *S2, *W, *loglik, *ab, *part, *scal;
     int32_t* ctrl;
     /* outputs */
     double* elbo;                /* [B, max_iter] every computed ELBO (the reference returns ELBO[:it]) */
@@ -148,7 +148,7 @@ typedef struct vb_bmm_args {
     const double* log_id_prior_kl;
     const double* s1_prior;      /* [n_var, K]                                                        */
     const double* s2_prior;
-    double *S1, *S2, *Wa, *Wb, *loglik, *part, *scal;
+    double *S1, *S2, *W, *loglik, *part, *scal;
     int32_t* ctrl;
     double* elbo;                /* [B, max_iter]                                                     */
 } vb_bmm_args;
@@ -164,11 +164,11 @@ int vb_bmm_step(const vb_counts* m, const vb_bmm_args* a, int phases, void* stre
  * column tables from GT_prob [n_var,K,G] and theta (add_doublet_GT :105-136, add_doublet_theta
  * :85-102) on the device, runs the cell-major logLik pass and the softmax with the doublet prior.
  *   loglik_out, prob_out: [n_cell, K2] with K2 = K + K(K-1)/2;  llr_out: [n_cell]
- *   Wa, Wb: workspace [n_var, K2] each;  log_prior_both: [id_prior_rows, K2]. */
+ *   W: workspace [n_var, 2, K2];  log_prior_both: [id_prior_rows, K2]. */
 int vb_vireo_doublet(const vb_counts* m, int n_donor, int n_gt, int ase_mode,
                      const double* gt_prob, const double* beta_mu, const double* beta_sum,
                      const double* log_prior_both, int id_prior_rows,
-                     double* Wa, double* Wb, double* loglik_out, double* prob_out, double* llr_out,
+                     double* W, double* loglik_out, double* prob_out, double* llr_out,
                      void* stream);
 
 /* Launch accounting.  Kernel classes: 0 k_snp, 1 k_theta, 2 k_gt, 3 k_cell, 4 k_elbo, 5 k_bmm_theta,

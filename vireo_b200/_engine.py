@@ -308,7 +308,7 @@ class VireoBatch:
         ws = _lib.WsSizes()
         _lib.check(_lib.load().vb_vireo_ws_sizes(counts.handle, K, G, B, int(self.ase), C.byref(ws)))
         self.S1, self.S2 = _zeros(ws.S, dev), _zeros(ws.S, dev)
-        self.Wa, self.Wb = _zeros(ws.W, dev), _zeros(ws.W, dev)
+        self.W = _zeros(ws.W, dev)
         self.loglik = _zeros(ws.loglik, dev)
         self.ab = _zeros(ws.ab, dev)
         self.part = _zeros(ws.part, dev)
@@ -328,7 +328,7 @@ class VireoBatch:
         a.id_prior_rows, a.theta_prior_rows = self.id_rows, self.thp_rows
         a.max_iter, a.min_iter, a.delay_fit_theta = int(max_iter), int(min_iter), int(delay)
         a.poll_every, a.epsilon_conv = int(poll_every), float(eps)
-        for name in ("id_prob", "gt_prob", "beta_mu", "beta_sum", "S1", "S2", "Wa", "Wb", "loglik", "ab", "part",
+        for name in ("id_prob", "gt_prob", "beta_mu", "beta_sum", "S1", "S2", "W", "loglik", "ab", "part",
                      "scal", "ctrl", "elbo"):
             setattr(a, name, getattr(self, name).data_ptr())
         a.log_id_prior, a.log_id_prior_kl = self.lidp.data_ptr(), self.lidp_kl.data_ptr()
@@ -439,7 +439,7 @@ class BmmBatch:
         ws = _lib.WsSizes()
         _lib.check(_lib.load().vb_bmm_ws_sizes(counts.handle, K, B, C.byref(ws)))
         self.S1, self.S2 = _zeros(ws.S, dev), _zeros(ws.S, dev)
-        self.Wa, self.Wb = _zeros(ws.W, dev), _zeros(ws.W, dev)
+        self.W = _zeros(ws.W, dev)
         self.loglik = _zeros(ws.loglik, dev)
         self.part = _zeros(ws.part, dev)
         self.scal = _zeros(ws.scal, dev)
@@ -452,7 +452,7 @@ class BmmBatch:
         a = _lib.BmmArgs()
         a.n_donor, a.n_batch, a.fix_beta_sum, a.id_prior_rows = self.K, self.B, int(self.fix_beta_sum), self.id_rows
         a.max_iter, a.min_iter, a.poll_every, a.epsilon_conv = int(max_iter), int(min_iter), int(poll_every), float(eps)
-        for name in ("id_prob", "beta_mu", "beta_sum", "S1", "S2", "Wa", "Wb", "loglik", "part", "scal", "ctrl",
+        for name in ("id_prob", "beta_mu", "beta_sum", "S1", "S2", "W", "loglik", "part", "scal", "ctrl",
                      "elbo"):
             setattr(a, name, getattr(self, name).data_ptr())
         a.log_id_prior, a.log_id_prior_kl = self.lidp.data_ptr(), self.lidp_kl.data_ptr()
@@ -497,11 +497,11 @@ def doublet_pass(counts, GT_prob, beta_mu, beta_sum, log_prior_both, ase):
     lp = np.asarray(log_prior_both, dtype=np.float64)
     lp = _compress_rows(lp)
     gt, mu, sm, lpd = _dev(GT_prob, dev), _dev(beta_mu, dev), _dev(beta_sum, dev), _dev(lp, dev)
-    Wa, Wb = _zeros(V * K2, dev), _zeros(V * K2, dev)
+    W = _zeros(2 * V * K2, dev)
     ll, pr, llr = _zeros(counts.n_cell * K2, dev), _zeros(counts.n_cell * K2, dev), _zeros(counts.n_cell, dev)
     with torch().cuda.device(dev):
         _lib.check(_lib.load().vb_vireo_doublet(counts.handle, K, G, int(bool(ase)), _ptr(gt), _ptr(mu), _ptr(sm),
-                                                _ptr(lpd), lp.shape[0], _ptr(Wa), _ptr(Wb), _ptr(ll), _ptr(pr),
+                                                _ptr(lpd), lp.shape[0], _ptr(W), _ptr(ll), _ptr(pr),
                                                 _ptr(llr), _stream(dev)))
     C_ = counts.n_cell
     return (ll.cpu().numpy().reshape(C_, K2), pr.cpu().numpy().reshape(C_, K2), llr.cpu().numpy())

@@ -32,7 +32,7 @@ class VireoArgs(C.Structure):
         ("id_prob", c_dp), ("gt_prob", c_dp), ("beta_mu", c_dp), ("beta_sum", c_dp),
         ("log_id_prior", c_dp), ("log_id_prior_kl", c_dp), ("log_gt_prior", c_dp), ("log_gt_prior_kl", c_dp),
         ("s1_prior", c_dp), ("s2_prior", c_dp),
-        ("S1", c_dp), ("S2", c_dp), ("Wa", c_dp), ("Wb", c_dp), ("loglik", c_dp), ("ab", c_dp), ("part", c_dp),
+        ("S1", c_dp), ("S2", c_dp), ("W", c_dp), ("loglik", c_dp), ("ab", c_dp), ("part", c_dp),
         ("scal", c_dp), ("ctrl", c_dp), ("elbo", c_dp),
     ]
 
@@ -44,7 +44,7 @@ class BmmArgs(C.Structure):
         ("epsilon_conv", C.c_double),
         ("id_prob", c_dp), ("beta_mu", c_dp), ("beta_sum", c_dp),
         ("log_id_prior", c_dp), ("log_id_prior_kl", c_dp), ("s1_prior", c_dp), ("s2_prior", c_dp),
-        ("S1", c_dp), ("S2", c_dp), ("Wa", c_dp), ("Wb", c_dp), ("loglik", c_dp), ("part", c_dp),
+        ("S1", c_dp), ("S2", c_dp), ("W", c_dp), ("loglik", c_dp), ("part", c_dp),
         ("scal", c_dp), ("ctrl", c_dp), ("elbo", c_dp),
     ]
 
@@ -64,7 +64,7 @@ SIGNATURES = {
     "vb_bmm_fit": (C.c_int, [C.c_void_p, C.POINTER(BmmArgs), C.c_void_p]),
     "vb_bmm_step": (C.c_int, [C.c_void_p, C.POINTER(BmmArgs), C.c_int, C.c_void_p]),
     "vb_vireo_doublet": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_int,
-                                   c_dp, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
+                                   c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
     "vb_launch_counts": (None, [C.POINTER(C.c_int64)]),
     "vb_profile_enable": (None, [C.c_int]),
     "vb_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -19,6 +19,51 @@
 #define VB_CTRL_N 4   // {done, it_next, last_it, n_decrease}
 #define VB_SCAL_N 8   // {ELBO, LB_p, KL_ID, KL_GT, KL_theta, -, -, -}
 
+// ----------------------------------------------------------------------------------------------
+// Tiled ("brick") format, one per pass orientation ("tiled kernels"):
+//   every nnz with 1 <= dp <= VB_EXPAND_MAX is expanded into dp UNIT records (ad of them carry the
+//   alternative allele), so a record is just "add gather row g into owner row o":
+//     cell pass: owner = cell j,               gather row = 2*snp + allele   (rows of the Wt table)
+//     SNP  pass: owner = 2*snp + allele,       gather row = cell j           (rows of ID_prob)
+//   Records are grouped into tiles (owner block of `rpb` rows) x (gather slab of `slab_rows` rows) and
+//   stored tile by tile as uint16 slab-local gather indices; each tile starts on a 16-byte boundary.
+//   seg[tile][0..rpb] are tile-local record offsets of the owner rows (row stride rpb+4, 16 B aligned).
+//   nnz with dp > VB_EXPAND_MAX stay in a small residual in the row (v1) layout ("heavy" stream).
+// ----------------------------------------------------------------------------------------------
+#define VB_EXPAND_MAX 4
+#define VB_TILE_THREADS 512
+#define VB_TILE_WARPS (VB_TILE_THREADS / 32)
+#define VB_TILE_MAX_DONOR 32
+
+struct TileSet {
+    int ok;                 // 0: this orientation cannot use the tiled kernels (reason in vb_last_error)
+    int64_t n_owner, n_gather;
+    int rpb, cpg, nb, nslab, slab_rows;
+    int gl;                 // lanes per group (each lane holds 2 donors)
+    int cpg_t;              // compiled accumulator rows per group (4 or 12)
+    int recb_max;           // largest tile record payload in bytes (multiple of 16)
+    int smem_bytes;         // dynamic shared memory of the kernel
+    int64_t n_rec;          // records incl. per-tile padding
+    uint32_t* tile_start;   // [nb*nslab + 1] record index where each tile starts
+    uint32_t* seg;          // [nb*nslab][rpb+4]
+    uint16_t* rec;          // [n_rec]
+};
+
+struct TileView {
+    int64_t n_owner, n_gather;
+    int rpb, cpg, nslab, slab_rows, gstride;   // gstride: doubles per gather row (= n_donor)
+    uint32_t slab_bytes, rec_off, ptr_off, buf_stride;
+    const uint32_t* __restrict__ tile_start;
+    const uint32_t* __restrict__ seg;
+    const uint16_t* __restrict__ rec;
+};
+
+struct TilePair {
+    int K;
+    TileSet A;   // cell pass
+    TileSet B;   // SNP pass
+};
+
 struct vb_counts {
     int device;
     int sm_count;
@@ -34,7 +79,26 @@ struct vb_counts {
     uint32_t* snp_dp;
     int grid_cell, grid_snp, grid_elem;
     int64_t bytes;
+    // residual of nnz with dp > VB_EXPAND_MAX (or ad > dp), same row layouts; built with the first tile set
+    int heavy_built;
+    int64_t Nh, N_unit, N_unit_rec;
+    int64_t* hcell_ptr;
+    int32_t* hcell_idx;
+    uint32_t* hcell_cnt;
+    uint32_t* hcell_dp;
+    int64_t* hsnp_ptr;
+    int32_t* hsnp_idx;
+    uint32_t* hsnp_cnt;
+    uint32_t* hsnp_dp;
+    // tile sets are specific to n_donor (slab size); a few are cached
+    TilePair tiles[4];
+    int n_tiles;
+    int tile_mode;          // 0 auto, 1 force rows (v1), 2 force tiles
 };
+
+// vb_tiles.cu
+const TilePair* vb_tiles_get(vb_counts* m, int K, cudaStream_t st);   // nullptr when the tiled path is not usable
+void vb_tiles_free(vb_counts* m);
 
 // what the kernels see of the staged counts
 struct CountsView {
@@ -60,7 +124,7 @@ struct EmP {
     double eps;
     double *R, *GT, *mu, *sum;
     const double *lidp, *lidp_kl, *lgtp, *lgtp_kl, *s1p, *s2p;
-    double *S1, *S2, *Wa, *Wb, *ll, *ab, *part, *scal, *elbo;
+    double *S1, *S2, *Wt, *ll, *ab, *part, *scal, *elbo;
     int* ctrl;
     // block-partial layout inside part[b * part_stride + ...]
     int64_t part_stride;

@@ -99,8 +99,8 @@ k_cell(const CountsView m, const EmP p, const int mode, const int k_off) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int sub = lane / KT, kl = lane % KT;
     const int K = p.K;
-    const double* __restrict__ Wa = p.Wa + (size_t)b * p.V * K;
-    const double* __restrict__ Wb = p.Wb + (size_t)b * p.V * K;
+    // Wt[V][2][K]: row 2i = table of a reference-allele read at SNP i (Wb), row 2i+1 = alternative allele (Wa)
+    const double* __restrict__ Wt = p.Wt + (size_t)b * p.V * 2 * K;
     double* __restrict__ R = p.R ? p.R + (size_t)b * p.C * K : nullptr;
     double* __restrict__ LL = p.ll + (size_t)b * p.C * K;
     double lbp = 0.0, klid = 0.0;
@@ -131,12 +131,12 @@ k_cell(const CountsView m, const EmP p, const int mode, const int k_off) {
                 if (src < n) {
                     int av, bv;
                     decode<WIDE>(cc, dd, av, bv);
-                    const size_t row = (size_t)i * K + k_off + kl;
+                    const size_t row = (size_t)i * 2 * K + k_off + kl;
 #pragma unroll
                     for (int r = 0; r < KR; ++r) {
                         if (k_off + kl + r * KT < K) {
-                            if (bv) acc[r] = axpy_count(bv, __ldg(Wb + row + r * KT), acc[r]);
-                            if (av) acc[r] = axpy_count(av, __ldg(Wa + row + r * KT), acc[r]);
+                            if (bv) acc[r] = axpy_count(bv, __ldg(Wt + row + r * KT), acc[r]);
+                            if (av) acc[r] = axpy_count(av, __ldg(Wt + row + K + r * KT), acc[r]);
                         }
                     }
                 }
@@ -436,12 +436,12 @@ __global__ void __launch_bounds__(VB_THREADS) k_gt(const EmP p, const int do_gt)
     double* __restrict__ GT = p.GT + (size_t)b * VK * G;
     const double* __restrict__ S1 = p.S1 + (size_t)b * VK;
     const double* __restrict__ S2 = p.S2 + (size_t)b * VK;
-    double* __restrict__ Wa = p.Wa + (size_t)b * VK;
-    double* __restrict__ Wb = p.Wb + (size_t)b * VK;
+    double* __restrict__ Wt = p.Wt + (size_t)b * VK * 2;
     __shared__ double sh[VB_WARPS];
     double kl = 0.0;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < VK; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = e / K;
+        const int k = (int)(e - i * K);
         const double* ab = p.ab + ((size_t)b * p.T + (p.ase ? i : 0)) * 2 * G;
         double pr[VB_MAX_GT];
         if (do_gt) {
@@ -473,8 +473,8 @@ __global__ void __launch_bounds__(VB_THREADS) k_gt(const EmP p, const int do_gt)
                 wb += pr[g] * ab[G + g];
                 if (pr[g] > 0.0) kl += pr[g] * (log(pr[g]) - p.lgtp_kl[(size_t)e * G + g]);
             }
-        Wa[e] = wa;
-        Wb[e] = wb;
+        Wt[(size_t)i * 2 * K + k] = wb;
+        Wt[(size_t)i * 2 * K + K + k] = wa;
     }
     const double t = block_sum(kl, sh);
     if (threadIdx.x == 0) p.part[(size_t)b * p.part_stride + p.off_klgt + blockIdx.x] = t;
@@ -494,8 +494,11 @@ __global__ void __launch_bounds__(VB_THREADS) k_bmm_theta(const EmP p, const int
         const size_t o = (size_t)b * VK + e;
         ThetaOut t = theta_finish(p, do_theta != 0, do_theta ? p.S1[o] : 0.0, do_theta ? p.S2[o] : 0.0, p.s1p[e],
                                   p.s2p[e], p.mu + o, p.sum + o);
-        p.Wa[o] = t.A;
-        p.Wb[o] = t.B;
+        const int64_t i = e / p.K;
+        const int k = (int)(e - i * p.K);
+        double* wt = p.Wt + (size_t)b * VK * 2 + (size_t)i * 2 * p.K + k;
+        wt[0] = t.B;
+        wt[p.K] = t.A;
         kl += t.kl;
     }
     const double t = block_sum(kl, sh);
@@ -604,7 +607,7 @@ __global__ void __launch_bounds__(64) k_doublet_theta(const double* __restrict__
 
 __global__ void __launch_bounds__(VB_THREADS) k_doublet_tables(const double* __restrict__ GT, const double* __restrict__ ab2,
                                                                int64_t V, int K, int G, int ase,
-                                                               double* __restrict__ Wa, double* __restrict__ Wb) {
+                                                               double* __restrict__ Wt) {
     const int G2 = G + G * (G - 1) / 2;
     const int K2 = K + K * (K - 1) / 2;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < V * K2; e += (int64_t)gridDim.x * blockDim.x) {
@@ -628,8 +631,8 @@ __global__ void __launch_bounds__(VB_THREADS) k_doublet_tables(const double* __r
                 for (int g2 = g1 + 1; g2 < G; ++g2) { pr[cc] = A[g1] * Bq[g2] + A[g2] * Bq[g1]; z += pr[cc]; ++cc; }   // :128-131
             for (int g = 0; g < G2; ++g) { const double pg = pr[g] / z; wa += pg * ab[g]; wb += pg * ab[G2 + g]; }   // :133
         }
-        Wa[e] = wa;
-        Wb[e] = wb;
+        Wt[(size_t)i * 2 * K2 + c] = wb;
+        Wt[(size_t)i * 2 * K2 + K2 + c] = wa;
     }
 }
 
@@ -746,10 +749,10 @@ static int fill_vireo(const vb_counts* m, const vb_vireo_args* a, EmP& p) {
     p.R = a->id_prob; p.GT = a->gt_prob; p.mu = a->beta_mu; p.sum = a->beta_sum;
     p.lidp = a->log_id_prior; p.lidp_kl = a->log_id_prior_kl; p.lgtp = a->log_gt_prior; p.lgtp_kl = a->log_gt_prior_kl;
     p.s1p = a->s1_prior; p.s2p = a->s2_prior;
-    p.S1 = a->S1; p.S2 = a->S2; p.Wa = a->Wa; p.Wb = a->Wb; p.ll = a->loglik; p.ab = a->ab; p.part = a->part;
+    p.S1 = a->S1; p.S2 = a->S2; p.Wt = a->W; p.ll = a->loglik; p.ab = a->ab; p.part = a->part;
     p.scal = a->scal; p.elbo = a->elbo; p.ctrl = a->ctrl;
     if (!p.R || !p.GT || !p.mu || !p.sum || !p.lidp || !p.lidp_kl || !p.lgtp || !p.lgtp_kl || !p.s1p || !p.s2p || !p.S1 ||
-        !p.S2 || !p.Wa || !p.Wb || !p.ll || !p.ab || !p.part || !p.scal || !p.ctrl) {
+        !p.S2 || !p.Wt || !p.ll || !p.ab || !p.part || !p.scal || !p.ctrl) {
         vb_set_error("NULL device pointer in vb_vireo_args");
         return VB_E_ARG;
     }
@@ -773,9 +776,9 @@ static int fill_bmm(const vb_counts* m, const vb_bmm_args* a, EmP& p) {
     p.max_iter = a->max_iter; p.min_iter = a->min_iter; p.eps = a->epsilon_conv;
     p.R = a->id_prob; p.mu = a->beta_mu; p.sum = a->beta_sum;
     p.lidp = a->log_id_prior; p.lidp_kl = a->log_id_prior_kl; p.s1p = a->s1_prior; p.s2p = a->s2_prior;
-    p.S1 = a->S1; p.S2 = a->S2; p.Wa = a->Wa; p.Wb = a->Wb; p.ll = a->loglik; p.part = a->part;
+    p.S1 = a->S1; p.S2 = a->S2; p.Wt = a->W; p.ll = a->loglik; p.part = a->part;
     p.scal = a->scal; p.elbo = a->elbo; p.ctrl = a->ctrl;
-    if (!p.R || !p.mu || !p.sum || !p.lidp || !p.lidp_kl || !p.s1p || !p.s2p || !p.S1 || !p.S2 || !p.Wa || !p.Wb ||
+    if (!p.R || !p.mu || !p.sum || !p.lidp || !p.lidp_kl || !p.s1p || !p.s2p || !p.S1 || !p.S2 || !p.Wt ||
         !p.ll || !p.part || !p.scal || !p.ctrl) {
         vb_set_error("NULL device pointer in vb_bmm_args");
         return VB_E_ARG;
@@ -793,7 +796,7 @@ static int ws_sizes(const vb_counts* m, int K, int G, int B, int T_is_V, vb_ws_s
     part_layout(m, p);
     const int64_t T = T_is_V ? m->V : 1;
     out->S = (int64_t)B * m->V * K;
-    out->W = (int64_t)B * m->V * K;
+    out->W = (int64_t)B * m->V * K * 2;
     out->loglik = (int64_t)B * m->C * K;
     out->ab = (int64_t)B * T * 2 * (G ? G : 1);
     out->part = (int64_t)B * p.part_stride;
@@ -913,9 +916,9 @@ extern "C" int vb_bmm_step(const vb_counts* m, const vb_bmm_args* a, int phases,
 extern "C" int vb_vireo_doublet(const vb_counts* m, int n_donor, int n_gt, int ase_mode,
                                 const double* gt_prob, const double* beta_mu, const double* beta_sum,
                                 const double* log_prior_both, int id_prior_rows,
-                                double* Wa, double* Wb, double* loglik_out, double* prob_out, double* llr_out,
+                                double* W, double* loglik_out, double* prob_out, double* llr_out,
                                 void* stream) {
-    if (!m || !gt_prob || !beta_mu || !beta_sum || !log_prior_both || !Wa || !Wb || !loglik_out || !prob_out || !llr_out) {
+    if (!m || !gt_prob || !beta_mu || !beta_sum || !log_prior_both || !W || !loglik_out || !prob_out || !llr_out) {
         vb_set_error("NULL argument");
         return VB_E_ARG;
     }
@@ -930,12 +933,12 @@ extern "C" int vb_vireo_doublet(const vb_counts* m, int n_donor, int n_gt, int a
     struct Free { void* p; ~Free() { cudaFree(p); } } fr{ab2};
     VB_LAUNCH(7, st, k_doublet_theta<<<(int)((T * G2 + 63) / 64 > 4096 ? 4096 : (T * G2 + 63) / 64), 64, 0, st>>>(beta_mu, beta_sum, T, G, ab2));
     VB_CUDA(cudaGetLastError());
-    VB_LAUNCH(7, st, k_doublet_tables<<<m->grid_elem, VB_THREADS, 0, st>>>(gt_prob, ab2, m->V, K, G, ase_mode, Wa, Wb));
+    VB_LAUNCH(7, st, k_doublet_tables<<<m->grid_elem, VB_THREADS, 0, st>>>(gt_prob, ab2, m->V, K, G, ase_mode, W));
     VB_CUDA(cudaGetLastError());
     // cell-major pass over column chunks of the K2-wide tables
     EmP p;
     memset(&p, 0, sizeof(p));
-    p.C = m->C; p.V = m->V; p.K = K2; p.B = 1; p.Wa = Wa; p.Wb = Wb; p.ll = loglik_out; p.id_rows = 1;
+    p.C = m->C; p.V = m->V; p.K = K2; p.B = 1; p.Wt = W; p.ll = loglik_out; p.id_rows = 1;
     const CountsView v = view_of(m);
     const int chunk = K2 <= 16 ? (K2 <= 2 ? 2 : K2 <= 4 ? 4 : K2 <= 8 ? 8 : 16) : 128;
     for (int k0 = 0; k0 < K2; k0 += chunk) {
