@@ -72,7 +72,10 @@ int vb_counts_create(int device, int64_t n_cell, int64_t n_var,
                      void* stream, vb_counts** out);
 void vb_counts_destroy(vb_counts* m);
 /* shape / layout queries: what = 0 n_cell, 1 n_var, 2 nnz, 3 wide flag, 4 device, 5 bytes resident,
- * 6 grid.x of the cell pass, 7 grid.x of the SNP pass, 8 grid.x of the elementwise (V*K) kernels */
+ * 6 grid.x of the cell pass (rows path), 7 grid.x of the SNP pass (rows path), 8 grid.x of the elementwise
+ * (V*K) kernels, 9 gather-stream formats built, 10 / 11 stream records of the cell / SNP pass, 12 residual
+ * (count >= 32) pairs, 13 bytes of the gather formats, 14 / 15 grid.x of the gather cell / SNP pass,
+ * 16 pairs carried by the streams */
 int64_t vb_counts_info(const vb_counts* m, int what);
 
 /* sum over nnz(DP>0) of float32(min(log C(dp, ad), 700)), accumulated in float64.
@@ -83,12 +86,14 @@ int vb_binom_const(const vb_counts* m, double* scratch, double* out_host, void* 
 /* Sizes of the per-call workspaces, in elements, for a batch of B restarts. */
 typedef struct vb_ws_sizes {
     int64_t S;        /* doubles: S1 and S2, each [B, n_var, K]                 */
-    int64_t W;        /* doubles: per-allele tables [B, n_var, 2, K]           */
+    int64_t W;        /* doubles: per-allele tables [B, n_var, 2, K] (gather path: K -> 16) */
     int64_t loglik;   /* doubles: [B, n_cell, K]                               */
     int64_t ab;       /* doubles: [B, T, 2*G] digamma differences              */
     int64_t part;     /* doubles: block partial sums                           */
     int64_t scal;     /* doubles: [B, 8] ELBO terms                            */
     int64_t ctrl;     /* int32:   [B, 4] {done, it, n_decrease, hit_max}       */
+    int64_t rpad;     /* doubles: ID_prob in 128-byte rows [B, n_cell, 16] (gather path, else 0) */
+    int64_t heavy;    /* doubles: residual sums [B, max(n_cell, 2 n_var), 16] (gather path, else 0) */
 } vb_ws_sizes;
 
 typedef struct vb_vireo_args {
@@ -117,6 +122,8 @@ typedef struct vb_vireo_args {
     int32_t* ctrl;
     /* outputs */
     double* elbo;                /* [B, max_iter] every computed ELBO (the reference returns ELBO[:it]) */
+    /* gather-path workspace (may be NULL when vb_vireo_ws_sizes reports 0) */
+    double *rpad, *heavy;
 } vb_vireo_args;
 
 int vb_vireo_ws_sizes(const vb_counts* m, int n_donor, int n_gt, int n_batch, int ase_mode, vb_ws_sizes* out);
@@ -151,6 +158,7 @@ typedef struct vb_bmm_args {
     double *S1, *S2, *W, *loglik, *part, *scal;
     int32_t* ctrl;
     double* elbo;                /* [B, max_iter]                                                     */
+    double *rpad, *heavy;        /* gather-path workspace (may be NULL when vb_bmm_ws_sizes reports 0) */
 } vb_bmm_args;
 
 int vb_bmm_ws_sizes(const vb_counts* m, int n_donor, int n_batch, vb_ws_sizes* out);
@@ -178,6 +186,12 @@ int vb_vireo_doublet(const vb_counts* m, int n_donor, int n_gt, int ase_mode,
 void vb_launch_counts(int64_t* n8);
 void vb_profile_enable(int on);
 int vb_profile_read(double* ms8, int64_t* n8);
+
+/* Kernel family for the two sparse passes: 0 = automatic (gather-stream kernels for large count matrices
+ * with n_donor <= 16, row kernels otherwise), 1 = row kernels (one warp per row, table gathered from L2),
+ * 2 = gather-stream kernels (lane per row, table streamed through shared memory by bulk async copies).
+ * Process-wide; affects workspaces sized afterwards. */
+void vb_set_path(int mode);
 
 const char* vb_last_error(void);
 /* library build info: "vireo_b200 <version> sm_100a" */

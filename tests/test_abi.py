@@ -31,10 +31,10 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    # field order/size as in the header: 14 int32 + 1 double + 19 pointers; 8 int32 + 1 double + 15 pointers
-    assert ctypes.sizeof(_lib.VireoArgs) == 14 * 4 + 8 + 19 * 8
-    assert ctypes.sizeof(_lib.BmmArgs) == 8 * 4 + 8 + 15 * 8
-    assert ctypes.sizeof(_lib.WsSizes) == 7 * 8
+    # field order/size as in the header: 14 int32 + 1 double + 21 pointers; 8 int32 + 1 double + 17 pointers
+    assert ctypes.sizeof(_lib.VireoArgs) == 14 * 4 + 8 + 21 * 8
+    assert ctypes.sizeof(_lib.BmmArgs) == 8 * 4 + 8 + 17 * 8
+    assert ctypes.sizeof(_lib.WsSizes) == 9 * 8
 
 
 def test_library_is_built_for_sm100a():

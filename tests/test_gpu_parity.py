@@ -32,6 +32,17 @@ def vb():
     return vireo_b200
 
 
+@pytest.fixture(autouse=True, params=["rows", "gather"])
+def kernel_path(request):
+    """Every parity test runs against both kernel families of the two sparse passes: the row kernels
+    (one warp per row, L2 gathers) and the gather-stream kernels (lane per row, table streamed through
+    shared memory by bulk async copies).  In production the choice is automatic (vb_set_path(0))."""
+    from vireo_b200 import _lib
+    _lib.set_path(request.param)
+    yield request.param
+    _lib.set_path("auto")
+
+
 def _quiet(fn, *a, **k):
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):

@@ -314,6 +314,8 @@ class VireoBatch:
         self.part = _zeros(ws.part, dev)
         self.scal = _zeros(ws.scal, dev)
         self.ctrl = _zeros(ws.ctrl, dev, t.int32)
+        self.rpad = _zeros(ws.rpad, dev)
+        self.heavy = _zeros(ws.heavy, dev)
         self.elbo = None
 
     def args(self, max_iter=1, min_iter=0, eps=1e-2, delay=0, poll_every=0):
@@ -329,7 +331,7 @@ class VireoBatch:
         a.max_iter, a.min_iter, a.delay_fit_theta = int(max_iter), int(min_iter), int(delay)
         a.poll_every, a.epsilon_conv = int(poll_every), float(eps)
         for name in ("id_prob", "gt_prob", "beta_mu", "beta_sum", "S1", "S2", "W", "loglik", "ab", "part",
-                     "scal", "ctrl", "elbo"):
+                     "scal", "ctrl", "elbo", "rpad", "heavy"):
             setattr(a, name, getattr(self, name).data_ptr())
         a.log_id_prior, a.log_id_prior_kl = self.lidp.data_ptr(), self.lidp_kl.data_ptr()
         a.log_gt_prior, a.log_gt_prior_kl = self.lgtp.data_ptr(), self.lgtp_kl.data_ptr()
@@ -444,6 +446,8 @@ class BmmBatch:
         self.part = _zeros(ws.part, dev)
         self.scal = _zeros(ws.scal, dev)
         self.ctrl = _zeros(ws.ctrl, dev, t.int32)
+        self.rpad = _zeros(ws.rpad, dev)
+        self.heavy = _zeros(ws.heavy, dev)
         self.elbo = None
 
     def args(self, max_iter=1, min_iter=0, eps=1e-2, poll_every=0):
@@ -453,7 +457,7 @@ class BmmBatch:
         a.n_donor, a.n_batch, a.fix_beta_sum, a.id_prior_rows = self.K, self.B, int(self.fix_beta_sum), self.id_rows
         a.max_iter, a.min_iter, a.poll_every, a.epsilon_conv = int(max_iter), int(min_iter), int(poll_every), float(eps)
         for name in ("id_prob", "beta_mu", "beta_sum", "S1", "S2", "W", "loglik", "part", "scal", "ctrl",
-                     "elbo"):
+                     "elbo", "rpad", "heavy"):
             setattr(a, name, getattr(self, name).data_ptr())
         a.log_id_prior, a.log_id_prior_kl = self.lidp.data_ptr(), self.lidp_kl.data_ptr()
         a.s1_prior, a.s2_prior = self.s1p.data_ptr(), self.s2p.data_ptr()

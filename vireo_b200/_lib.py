@@ -18,7 +18,7 @@ c_dp = C.c_void_p  # device pointer
 
 
 class WsSizes(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in ("S", "W", "loglik", "ab", "part", "scal", "ctrl")]
+    _fields_ = [(n, C.c_int64) for n in ("S", "W", "loglik", "ab", "part", "scal", "ctrl", "rpad", "heavy")]
 
 
 class VireoArgs(C.Structure):
@@ -33,7 +33,7 @@ class VireoArgs(C.Structure):
         ("log_id_prior", c_dp), ("log_id_prior_kl", c_dp), ("log_gt_prior", c_dp), ("log_gt_prior_kl", c_dp),
         ("s1_prior", c_dp), ("s2_prior", c_dp),
         ("S1", c_dp), ("S2", c_dp), ("W", c_dp), ("loglik", c_dp), ("ab", c_dp), ("part", c_dp),
-        ("scal", c_dp), ("ctrl", c_dp), ("elbo", c_dp),
+        ("scal", c_dp), ("ctrl", c_dp), ("elbo", c_dp), ("rpad", c_dp), ("heavy", c_dp),
     ]
 
 
@@ -45,7 +45,7 @@ class BmmArgs(C.Structure):
         ("id_prob", c_dp), ("beta_mu", c_dp), ("beta_sum", c_dp),
         ("log_id_prior", c_dp), ("log_id_prior_kl", c_dp), ("s1_prior", c_dp), ("s2_prior", c_dp),
         ("S1", c_dp), ("S2", c_dp), ("W", c_dp), ("loglik", c_dp), ("part", c_dp),
-        ("scal", c_dp), ("ctrl", c_dp), ("elbo", c_dp),
+        ("scal", c_dp), ("ctrl", c_dp), ("elbo", c_dp), ("rpad", c_dp), ("heavy", c_dp),
     ]
 
 
@@ -65,6 +65,7 @@ SIGNATURES = {
     "vb_bmm_step": (C.c_int, [C.c_void_p, C.POINTER(BmmArgs), C.c_int, C.c_void_p]),
     "vb_vireo_doublet": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_int,
                                    c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
+    "vb_set_path": (None, [C.c_int]),
     "vb_launch_counts": (None, [C.POINTER(C.c_int64)]),
     "vb_profile_enable": (None, [C.c_int]),
     "vb_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -97,7 +98,14 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    env = os.environ.get("VIREO_B200_PATH", "auto").lower()
+    lib.vb_set_path({"auto": 0, "rows": 1, "gather": 2}.get(env, 0))
     return lib
+
+
+def set_path(mode):
+    """'auto' | 'rows' | 'gather': kernel family of the two sparse passes (see vb_set_path)."""
+    load().vb_set_path({"auto": 0, "rows": 1, "gather": 2}[mode])
 
 
 KERNEL_CLASSES = ("k_snp", "k_theta", "k_gt", "k_cell", "k_elbo", "k_bmm_theta", "k_terms", "doublet")

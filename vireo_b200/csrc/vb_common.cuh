@@ -20,48 +20,54 @@
 #define VB_SCAL_N 8   // {ELBO, LB_p, KL_ID, KL_GT, KL_theta, -, -, -}
 
 // ----------------------------------------------------------------------------------------------
-// Tiled ("brick") format, one per pass orientation ("tiled kernels"):
-//   every nnz with 1 <= dp <= VB_EXPAND_MAX is expanded into dp UNIT records (ad of them carry the
-//   alternative allele), so a record is just "add gather row g into owner row o":
-//     cell pass: owner = cell j,               gather row = 2*snp + allele   (rows of the Wt table)
-//     SNP  pass: owner = 2*snp + allele,       gather row = cell j           (rows of ID_prob)
-//   Records are grouped into tiles (owner block of `rpb` rows) x (gather slab of `slab_rows` rows) and
-//   stored tile by tile as uint16 slab-local gather indices; each tile starts on a 16-byte boundary.
-//   seg[tile][0..rpb] are tile-local record offsets of the owner rows (row stride rpb+4, 16 B aligned).
-//   nnz with dp > VB_EXPAND_MAX stay in a small residual in the row (v1) layout ("heavy" stream).
+// Gather-stream format ("ring-slab gather kernels"), one per pass orientation:
+//     cell pass (A): owner = cell j,            gather row = 2*snp + allele  (rows of the W table)
+//     SNP  pass (B): owner = 2*snp + allele,    gather row = cell j          (rows of ID_prob)
+//   with allele 0 = reference reads (count dp-ad), allele 1 = alternative reads (count ad).
+//   Every (owner, gather row, count) with 1 <= count <= 31 is one 16-bit record
+//       bits 15..5  delta = gather row - gather row of the owner's previous record (first: - 0)
+//       bits  4..0  count (0 = "skip": advance `delta` rows, add nothing; bridges gaps > 2047)
+//   An owner's records form a stream in ascending gather-row order.  Owners are sorted by stream
+//   length (descending) and packed 32 to a warp slot; a warp slot's streams are interleaved in
+//   256-byte blocks [block][lane][4 records] so that lanes running in step read coalesced.
+//   Counts >= 32 go to a small residual CSR ("heavy" records) handled by k_heavy.
 // ----------------------------------------------------------------------------------------------
-#define VB_EXPAND_MAX 4
-#define VB_TILE_THREADS 512
-#define VB_TILE_WARPS (VB_TILE_THREADS / 32)
-#define VB_TILE_MAX_DONOR 32
+#define VB_REC_COUNT_BITS 5
+#define VB_REC_MAX_COUNT 31
+#define VB_REC_MAX_DELTA 2047
+#define VB_ROW_DOUBLES 16                 // every gather-table row is 16 doubles = 128 bytes (all 32 banks)
+#define VB_SLAB_ROWS 128                  // rows per bulk copy (16 KB)
+#define VB_RING_SLABS 12                  // slabs resident in shared memory (192 KB)
+#define VB_RING_ROWS (VB_SLAB_ROWS * VB_RING_SLABS)
+#define VB_GATHER_MAX_WARPS 22            // consumer warps per CTA (+1 producer warp)
 
-struct TileSet {
-    int ok;                 // 0: this orientation cannot use the tiled kernels (reason in vb_last_error)
+struct GatherSet {
+    int built;
     int64_t n_owner, n_gather;
-    int rpb, cpg, nb, nslab, slab_rows;
-    int gl;                 // lanes per group (each lane holds 2 donors)
-    int cpg_t;              // compiled accumulator rows per group (4 or 12)
-    int recb_max;           // largest tile record payload in bytes (multiple of 16)
-    int smem_bytes;         // dynamic shared memory of the kernel
-    int64_t n_rec;          // records incl. per-tile padding
-    uint32_t* tile_start;   // [nb*nslab + 1] record index where each tile starts
-    uint32_t* seg;          // [nb*nslab][rpb+4]
-    uint16_t* rec;          // [n_rec]
+    int64_t n_slot;          // warp slots = ceil(n_owner / 32)
+    int64_t n_rec;           // stream records incl. skips (excl. padding)
+    int64_t n_light;         // (owner, gather row) pairs carried by the streams
+    int64_t n_heavy;         // pairs in the residual
+    int64_t n_block;         // 256-byte stream blocks
+    int32_t* perm;           // [n_slot*32] owner id of each lane, -1 = padding
+    uint32_t* len;           // [n_slot*32] stream length of each lane
+    uint32_t* slot_blk;      // [n_slot+1] first block of each warp slot
+    uint16_t* rec;           // [n_block*128]
+    int64_t* hptr;           // [n_owner+1] residual CSR
+    int32_t* hrow;
+    uint32_t* hcnt;
+    int64_t bytes;
 };
 
-struct TileView {
-    int64_t n_owner, n_gather;
-    int rpb, cpg, nslab, slab_rows, gstride;   // gstride: doubles per gather row (= n_donor)
-    uint32_t slab_bytes, rec_off, ptr_off, buf_stride;
-    const uint32_t* __restrict__ tile_start;
-    const uint32_t* __restrict__ seg;
+struct GatherView {
+    int64_t n_owner, n_gather, n_slot;
+    const int32_t* __restrict__ perm;
+    const uint32_t* __restrict__ len;
+    const uint32_t* __restrict__ slot_blk;
     const uint16_t* __restrict__ rec;
-};
-
-struct TilePair {
-    int K;
-    TileSet A;   // cell pass
-    TileSet B;   // SNP pass
+    const int64_t* __restrict__ hptr;
+    const int32_t* __restrict__ hrow;
+    const uint32_t* __restrict__ hcnt;
 };
 
 struct vb_counts {
@@ -79,26 +85,15 @@ struct vb_counts {
     uint32_t* snp_dp;
     int grid_cell, grid_snp, grid_elem;
     int64_t bytes;
-    // residual of nnz with dp > VB_EXPAND_MAX (or ad > dp), same row layouts; built with the first tile set
-    int heavy_built;
-    int64_t Nh, N_unit, N_unit_rec;
-    int64_t* hcell_ptr;
-    int32_t* hcell_idx;
-    uint32_t* hcell_cnt;
-    uint32_t* hcell_dp;
-    int64_t* hsnp_ptr;
-    int32_t* hsnp_idx;
-    uint32_t* hsnp_cnt;
-    uint32_t* hsnp_dp;
-    // tile sets are specific to n_donor (slab size); a few are cached
-    TilePair tiles[4];
-    int n_tiles;
-    int tile_mode;          // 0 auto, 1 force rows (v1), 2 force tiles
+    // gather-stream formats (built lazily, independent of n_donor)
+    GatherSet gA;           // cell pass
+    GatherSet gB;           // SNP pass
+    int gather_failed;      // a build attempt failed (message in vb_last_error); rows path is used
 };
 
-// vb_tiles.cu
-const TilePair* vb_tiles_get(vb_counts* m, int K, cudaStream_t st);   // nullptr when the tiled path is not usable
-void vb_tiles_free(vb_counts* m);
+// vb_gather.cu
+int vb_gather_build(vb_counts* m, cudaStream_t st);      // builds gA and gB once
+void vb_gather_free(vb_counts* m);
 
 // what the kernels see of the staged counts
 struct CountsView {
@@ -126,6 +121,10 @@ struct EmP {
     const double *lidp, *lidp_kl, *lgtp, *lgtp_kl, *s1p, *s2p;
     double *S1, *S2, *Wt, *ll, *ab, *part, *scal, *elbo;
     int* ctrl;
+    // gather path (vb_gather.cu): Wt is then [B, 2V, 16] (rows of 128 bytes, columns replicated 16/KT times),
+    // RP the same layout of ID_prob [B, C, 16], H the residual sums [B, max(C, 2V), 16]
+    int tiled, KT;
+    double *RP, *H;
     // block-partial layout inside part[b * part_stride + ...]
     int64_t part_stride;
     int off_theta, off_klgt, off_cell, off_klth;
@@ -194,6 +193,36 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
     return t;
 }
 #endif
+
+#ifdef __CUDACC__
+// theta_mode: 0 never, 1 always, 2 when learn_theta and the device iteration counter >= delay
+__device__ __forceinline__ bool vb_theta_on(const EmP& p, int b, int theta_mode) {
+    if (theta_mode == 1) return true;
+    if (theta_mode == 2) return p.learn_theta && p.ctrl[b * VB_CTRL_N + 1] >= p.delay;
+    return false;
+}
+#endif
+
+// launch accounting (vb_em.cu): every kernel launch of the EM path goes through VB_LAUNCH, which counts it
+// and, when profiling is enabled, brackets it with CUDA events on the launching stream.
+// classes: 0 SNP pass, 1 k_theta, 2 k_gt, 3 cell pass, 4 k_elbo, 5 k_bmm_theta, 6 k_terms, 7 helpers
+void vb_launch_begin(int cls, cudaStream_t st, cudaEvent_t* e0, cudaEvent_t* e1);
+void vb_launch_end(int cls, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1);
+#define VB_LAUNCH(cls, st, ...)                                         \
+    do {                                                                \
+        cudaEvent_t e0__ = nullptr, e1__ = nullptr;                     \
+        vb_launch_begin(cls, st, &e0__, &e1__);                         \
+        __VA_ARGS__;                                                    \
+        vb_launch_end(cls, st, e0__, e1__);                             \
+    } while (0)
+
+// vb_gather.cu
+void vb_gather_geometry(const vb_counts* m, const GatherSet& g, int* grid, int* nwarps);
+int vb_gather_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, double* plain_out,
+                     cudaStream_t st);
+int vb_pad_rows_launch(const vb_counts* m, const double* src, int64_t n_row, int K, int KT, int B, double* dst,
+                       cudaStream_t st);
+enum { GM_CELL = 0, GM_CELL_LL = 1, GM_SNP = 2, GM_PLAIN = 3 };
 
 // error plumbing -------------------------------------------------------------------------------
 void vb_set_error(const char* fmt, ...);

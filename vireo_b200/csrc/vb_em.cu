@@ -33,21 +33,22 @@ static bool g_prof_on = false;
 static std::vector<ProfEvent> g_prof_events;
 static int64_t g_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-#define VB_LAUNCH(cls, st, ...)                                         \
-    do {                                                                \
-        cudaEvent_t e0__ = nullptr, e1__ = nullptr;                     \
-        if (g_prof_on) {                                                \
-            cudaEventCreate(&e0__);                                     \
-            cudaEventCreate(&e1__);                                     \
-            cudaEventRecord(e0__, st);                                  \
-        }                                                               \
-        __VA_ARGS__;                                                    \
-        if (g_prof_on) {                                                \
-            cudaEventRecord(e1__, st);                                  \
-            g_prof_events.push_back(ProfEvent{cls, e0__, e1__});        \
-        }                                                               \
-        g_launches[cls] += 1;                                           \
-    } while (0)
+void vb_launch_begin(int cls, cudaStream_t st, cudaEvent_t* e0, cudaEvent_t* e1) {
+    (void)cls;
+    if (g_prof_on) {
+        cudaEventCreate(e0);
+        cudaEventCreate(e1);
+        cudaEventRecord(*e0, st);
+    }
+}
+
+void vb_launch_end(int cls, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+    if (g_prof_on && e0 && e1) {
+        cudaEventRecord(e1, st);
+        g_prof_events.push_back(ProfEvent{cls, e0, e1});
+    }
+    g_launches[cls] += 1;
+}
 
 extern "C" void vb_profile_enable(int on) { g_prof_on = on != 0; }
 
@@ -216,18 +217,12 @@ k_cell(const CountsView m, const EmP p, const int mode, const int k_off) {
 // k_snp: one warp per SNP.  Gathers ID_prob rows by cell id; two accumulators per column.
 // theta_mode: 0 never, 1 always, 2 when learn_theta and the device iteration counter >= delay
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool theta_on(const EmP& p, int b, int theta_mode) {
-    if (theta_mode == 1) return true;
-    if (theta_mode == 2) return p.learn_theta && p.ctrl[b * VB_CTRL_N + 1] >= p.delay;
-    return false;
-}
-
 template <int KT, int KR, bool WIDE>
 __global__ void __launch_bounds__(VB_THREADS)
 k_snp(const CountsView m, const EmP p, const int theta_mode) {
     const int b = blockIdx.y;
     if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
-    const bool do_theta = !p.bmm && theta_on(p, b, theta_mode);
+    const bool do_theta = !p.bmm && vb_theta_on(p, b, theta_mode);
     if (!p.bmm && !do_theta && !p.learn_gt && theta_mode == 2) return;   // nothing consumes S1/S2 this iteration
     constexpr int NPW = 32 / KT;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -366,7 +361,7 @@ __device__ __forceinline__ ThetaOut theta_finish(const EmP& p, bool do_theta, do
 __global__ void __launch_bounds__(2 * VB_MAX_GT * 32) k_theta(const EmP p, const int theta_mode) {
     const int b = blockIdx.y;
     if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
-    const bool do_theta = theta_on(p, b, theta_mode);
+    const bool do_theta = vb_theta_on(p, b, theta_mode);
     const int G = p.G;
     __shared__ double tot[2 * VB_MAX_GT];
     __shared__ double kls[VB_MAX_GT];
@@ -400,7 +395,7 @@ __global__ void __launch_bounds__(2 * VB_MAX_GT * 32) k_theta(const EmP p, const
 __global__ void __launch_bounds__(VB_THREADS) k_theta_ase(const EmP p, const int theta_mode) {
     const int b = blockIdx.y;
     if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
-    const bool do_theta = theta_on(p, b, theta_mode);
+    const bool do_theta = vb_theta_on(p, b, theta_mode);
     const int G = p.G;
     __shared__ double sh[VB_WARPS];
     double kl = 0.0;
@@ -473,8 +468,14 @@ __global__ void __launch_bounds__(VB_THREADS) k_gt(const EmP p, const int do_gt)
                 wb += pr[g] * ab[G + g];
                 if (pr[g] > 0.0) kl += pr[g] * (log(pr[g]) - p.lgtp_kl[(size_t)e * G + g]);
             }
-        Wt[(size_t)i * 2 * K + k] = wb;
-        Wt[(size_t)i * 2 * K + K + k] = wa;
+        if (p.tiled) {
+            // gather-table rows of 128 bytes, columns replicated 16/KT times (vb_gather.cu)
+            double* w0 = p.Wt + ((size_t)b * p.V + i) * 2 * VB_ROW_DOUBLES;
+            for (int c = k; c < VB_ROW_DOUBLES; c += p.KT) { w0[c] = wb; w0[VB_ROW_DOUBLES + c] = wa; }
+        } else {
+            Wt[(size_t)i * 2 * K + k] = wb;
+            Wt[(size_t)i * 2 * K + K + k] = wa;
+        }
     }
     const double t = block_sum(kl, sh);
     if (threadIdx.x == 0) p.part[(size_t)b * p.part_stride + p.off_klgt + blockIdx.x] = t;
@@ -496,9 +497,14 @@ __global__ void __launch_bounds__(VB_THREADS) k_bmm_theta(const EmP p, const int
                                   p.s2p[e], p.mu + o, p.sum + o);
         const int64_t i = e / p.K;
         const int k = (int)(e - i * p.K);
-        double* wt = p.Wt + (size_t)b * VK * 2 + (size_t)i * 2 * p.K + k;
-        wt[0] = t.B;
-        wt[p.K] = t.A;
+        if (p.tiled) {
+            double* w0 = p.Wt + ((size_t)b * p.V + i) * 2 * VB_ROW_DOUBLES;
+            for (int c = k; c < VB_ROW_DOUBLES; c += p.KT) { w0[c] = t.B; w0[VB_ROW_DOUBLES + c] = t.A; }
+        } else {
+            double* wt = p.Wt + (size_t)b * VK * 2 + (size_t)i * 2 * p.K + k;
+            wt[0] = t.B;
+            wt[p.K] = t.A;
+        }
         kl += t.kl;
     }
     const double t = block_sum(kl, sh);
@@ -704,6 +710,7 @@ static bool tile_for(int K, int& KT, int& KR) {
     } while (0)
 
 static int launch_cell(const vb_counts* m, const EmP& p, int mode, cudaStream_t st) {
+    if (p.tiled) return vb_gather_launch(m, p, 0, mode == 0 ? GM_CELL : GM_CELL_LL, 0, nullptr, st);
     int KT, KR;
     if (!tile_for(p.K, KT, KR)) { vb_set_error("n_donor=%d outside [1, %d]", p.K, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
     const CountsView v = view_of(m);
@@ -714,6 +721,7 @@ static int launch_cell(const vb_counts* m, const EmP& p, int mode, cudaStream_t 
 }
 
 static int launch_snp(const vb_counts* m, const EmP& p, int theta_mode, cudaStream_t st) {
+    if (p.tiled) return vb_gather_launch(m, p, 1, GM_SNP, theta_mode, nullptr, st);
     int KT, KR;
     if (!tile_for(p.K, KT, KR)) { vb_set_error("n_donor=%d outside [1, %d]", p.K, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
     const CountsView v = view_of(m);
@@ -723,15 +731,46 @@ static int launch_snp(const vb_counts* m, const EmP& p, int theta_mode, cudaStre
     return VB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// path selection: rows (v1, one warp per row, L2 gathers) or gather (vb_gather.cu, ring-slab streams)
+// ---------------------------------------------------------------------------------------------
+static int g_path = 0;                       // 0 auto, 1 rows, 2 gather
+#define VB_GATHER_MIN_NNZ (4ll << 20)        // below this the passes are launch/latency bound either way
+
+extern "C" void vb_set_path(int mode) { g_path = mode < 0 || mode > 2 ? 0 : mode; }
+
+// *use = 1 when the gather kernels serve this (counts, K); builds the formats on first use
+static int want_gather(const vb_counts* mc, int K, int* use) {
+    vb_counts* m = const_cast<vb_counts*>(mc);
+    *use = 0;
+    if (g_path == 1 || K > VB_ROW_DOUBLES) return VB_OK;
+    if (g_path == 0 && (m->N < VB_GATHER_MIN_NNZ || m->gather_failed)) return VB_OK;
+    const int rc = vb_gather_build(m, 0);
+    if (rc) return g_path == 2 ? rc : VB_OK;
+    if (g_path == 0) {
+        // mostly large counts (e.g. mitochondrial clone data): the residual kernel would do all the work
+        const int64_t pairs = m->gA.n_light + m->gA.n_heavy;
+        if (m->gA.n_heavy * 4 > pairs) return VB_OK;
+    }
+    *use = 1;
+    return VB_OK;
+}
+
+static int kt_for(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : 16); }
+
 static void part_layout(const vb_counts* m, EmP& p) {
-    p.n_snpblk = m->grid_snp;
+    int ga = 0, gb = 0, nw;
+    if (m->gA.built) { vb_gather_geometry(m, m->gA, &ga, &nw); vb_gather_geometry(m, m->gB, &gb, &nw); }
+    p.n_snpblk = p.tiled ? gb : m->grid_snp;
     p.n_elemblk = m->grid_elem;
-    p.n_cellblk = m->grid_cell;
+    p.n_cellblk = p.tiled ? ga : m->grid_cell;
     p.n_klth = (p.bmm || p.ase) ? m->grid_elem : 1;
+    const int cap_snp = gb > m->grid_snp ? gb : m->grid_snp;
+    const int cap_cell = ga > m->grid_cell ? ga : m->grid_cell;
     p.off_theta = 0;
-    p.off_klgt = p.off_theta + p.n_snpblk * 2 * VB_MAX_GT;
+    p.off_klgt = p.off_theta + cap_snp * 2 * VB_MAX_GT;
     p.off_cell = p.off_klgt + p.n_elemblk;
-    p.off_klth = p.off_cell + 2 * p.n_cellblk;
+    p.off_klth = p.off_cell + 2 * cap_cell;
     p.part_stride = p.off_klth + m->grid_elem;
 }
 
@@ -755,6 +794,13 @@ static int fill_vireo(const vb_counts* m, const vb_vireo_args* a, EmP& p) {
         !p.S2 || !p.Wt || !p.ll || !p.ab || !p.part || !p.scal || !p.ctrl) {
         vb_set_error("NULL device pointer in vb_vireo_args");
         return VB_E_ARG;
+    }
+    {
+        int use = 0;
+        const int rc = want_gather(m, p.K, &use);
+        if (rc) return rc;
+        p.tiled = use; p.KT = kt_for(p.K); p.RP = a->rpad; p.H = a->heavy;
+        if (use && (!p.RP || !p.H)) { vb_set_error("rpad / heavy workspace is NULL (see vb_vireo_ws_sizes)"); return VB_E_ARG; }
     }
     if ((p.id_rows != 1 && p.id_rows != m->C) || (p.thp_rows != 1 && p.thp_rows != p.T)) {
         vb_set_error("prior rows must be 1 or the full extent");
@@ -783,6 +829,13 @@ static int fill_bmm(const vb_counts* m, const vb_bmm_args* a, EmP& p) {
         vb_set_error("NULL device pointer in vb_bmm_args");
         return VB_E_ARG;
     }
+    {
+        int use = 0;
+        const int rc = want_gather(m, p.K, &use);
+        if (rc) return rc;
+        p.tiled = use; p.KT = kt_for(p.K); p.RP = a->rpad; p.H = a->heavy;
+        if (use && (!p.RP || !p.H)) { vb_set_error("rpad / heavy workspace is NULL (see vb_bmm_ws_sizes)"); return VB_E_ARG; }
+    }
     if (p.id_rows != 1 && p.id_rows != m->C) { vb_set_error("id_prior_rows must be 1 or n_cell"); return VB_E_ARG; }
     part_layout(m, p);
     return VB_OK;
@@ -793,10 +846,17 @@ static int ws_sizes(const vb_counts* m, int K, int G, int B, int T_is_V, vb_ws_s
     EmP p;
     memset(&p, 0, sizeof(p));
     p.bmm = G == 0; p.ase = T_is_V;
+    int use = 0;
+    const int rc = want_gather(m, K, &use);
+    if (rc) return rc;
+    p.tiled = use;
     part_layout(m, p);
     const int64_t T = T_is_V ? m->V : 1;
+    const int64_t Kw = use ? VB_ROW_DOUBLES : K;
     out->S = (int64_t)B * m->V * K;
-    out->W = (int64_t)B * m->V * K * 2;
+    out->W = (int64_t)B * m->V * Kw * 2;
+    out->rpad = use ? (int64_t)B * m->C * VB_ROW_DOUBLES : 0;
+    out->heavy = use ? (int64_t)B * (m->C > 2 * m->V ? m->C : 2 * m->V) * VB_ROW_DOUBLES : 0;
     out->loglik = (int64_t)B * m->C * K;
     out->ab = (int64_t)B * T * 2 * (G ? G : 1);
     out->part = (int64_t)B * p.part_stride;
@@ -829,7 +889,7 @@ static int vireo_iteration(const vb_counts* m, const EmP& p, int phases, bool in
     VB_CUDA(cudaGetLastError());
     if (phases & VB_PH_ID) { if ((rc = launch_cell(m, p, 0, st))) return rc; }
     else if (phases & VB_PH_LOGLIK) { if ((rc = launch_cell(m, p, 1, st))) return rc; }
-    else if (phases & VB_PH_ELBO) { VB_LAUNCH(6, st, k_terms<<<dim3(m->grid_cell, p.B), VB_THREADS, 0, st>>>(p)); VB_CUDA(cudaGetLastError()); }
+    else if (phases & VB_PH_ELBO) { VB_LAUNCH(6, st, k_terms<<<dim3(p.n_cellblk, p.B), VB_THREADS, 0, st>>>(p)); VB_CUDA(cudaGetLastError()); }
     if (phases & VB_PH_ELBO) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, in_loop ? 1 : 0)); VB_CUDA(cudaGetLastError()); }
     return VB_OK;
 }
@@ -843,7 +903,7 @@ static int bmm_iteration(const vb_counts* m, const EmP& p, int phases, bool in_l
     VB_CUDA(cudaGetLastError());
     if (phases & VB_PH_ID) { if ((rc = launch_cell(m, p, 0, st))) return rc; }
     else if (phases & VB_PH_LOGLIK) { if ((rc = launch_cell(m, p, 1, st))) return rc; }
-    else if (phases & VB_PH_ELBO) { VB_LAUNCH(6, st, k_terms<<<dim3(m->grid_cell, p.B), VB_THREADS, 0, st>>>(p)); VB_CUDA(cudaGetLastError()); }
+    else if (phases & VB_PH_ELBO) { VB_LAUNCH(6, st, k_terms<<<dim3(p.n_cellblk, p.B), VB_THREADS, 0, st>>>(p)); VB_CUDA(cudaGetLastError()); }
     if (phases & VB_PH_ELBO) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, in_loop ? 1 : 0)); VB_CUDA(cudaGetLastError()); }
     return VB_OK;
 }
@@ -863,6 +923,10 @@ static int run_loop(const vb_counts* m, const EmP& p, int poll_every, cudaStream
         g_pin_n = n_ctrl;
     }
     VB_CUDA(cudaMemsetAsync(p.ctrl, 0, n_ctrl * sizeof(int32_t), st));
+    if (p.tiled) {   // the SNP pass gathers ID_prob from its 128-byte-row copy
+        const int rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.B, p.RP, st);
+        if (rc) return rc;
+    }
     if (poll_every <= 0) poll_every = 16;
     const int all = VB_PH_SNP | VB_PH_THETA | VB_PH_GT | VB_PH_ID | VB_PH_ELBO;
     for (int it = 0; it < p.max_iter; ++it) {
@@ -893,6 +957,10 @@ extern "C" int vb_vireo_step(const vb_counts* m, const vb_vireo_args* a, int pha
     if (rc) return rc;
     VB_CUDA(cudaSetDevice(m->device));
     p.ctrl = nullptr;                       // single phases never consult the loop state
+    if (p.tiled && (phases & VB_PH_SNP)) {
+        rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.B, p.RP, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     return vireo_iteration(m, p, phases, false, (cudaStream_t)stream);
 }
 
@@ -910,6 +978,10 @@ extern "C" int vb_bmm_step(const vb_counts* m, const vb_bmm_args* a, int phases,
     if (rc) return rc;
     VB_CUDA(cudaSetDevice(m->device));
     p.ctrl = nullptr;
+    if (p.tiled && (phases & VB_PH_SNP)) {
+        rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.B, p.RP, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     return bmm_iteration(m, p, phases, false, (cudaStream_t)stream);
 }
 

@@ -168,6 +168,7 @@ extern "C" void vb_counts_destroy(vb_counts* m) {
     cudaSetDevice(m->device);
     cudaFree(m->cell_ptr); cudaFree(m->cell_idx); cudaFree(m->cell_cnt); cudaFree(m->cell_dp);
     cudaFree(m->snp_ptr); cudaFree(m->snp_idx); cudaFree(m->snp_cnt); cudaFree(m->snp_dp);
+    vb_gather_free(m);
     delete m;
 }
 
@@ -183,6 +184,14 @@ extern "C" int64_t vb_counts_info(const vb_counts* m, int what) {
         case 6: return m->grid_cell;
         case 7: return m->grid_snp;
         case 8: return m->grid_elem;
+        case 9: return m->gA.built && m->gB.built;
+        case 10: return m->gA.n_rec;
+        case 11: return m->gB.n_rec;
+        case 12: return m->gA.n_heavy;
+        case 13: return m->gA.bytes + m->gB.bytes;
+        case 14: { int g = 0, w = 0; if (m->gA.built) vb_gather_geometry(m, m->gA, &g, &w); return g; }
+        case 15: { int g = 0, w = 0; if (m->gB.built) vb_gather_geometry(m, m->gB, &g, &w); return g; }
+        case 16: return m->gA.n_light;
         default: return -1;
     }
 }
