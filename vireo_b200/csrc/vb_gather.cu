@@ -20,6 +20,7 @@
 // per SM), not HBM: the record streams are 2 B per nnz-allele pair.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <stdlib.h>
 #include <string.h>
 
 #include "vb_common.cuh"
@@ -371,6 +372,7 @@ k_pad_rows(const double* __restrict__ src, int64_t n_row, int K, int KT, double*
 // k_gather
 // ---------------------------------------------------------------------------------------------
 #define VB_G_EPOCH 8
+#define VB_G_LAG_ROWS ((VB_RING_SLABS - 3) * VB_SLAB_ROWS)
 #define VB_G_RING_BYTES (VB_RING_ROWS * VB_ROW_DOUBLES * 8)
 #define VB_G_SLAB_BYTES (VB_SLAB_ROWS * VB_ROW_DOUBLES * 8)
 #define VB_G_RED_DOUBLES (2 * VB_MAX_GT)
@@ -387,6 +389,8 @@ struct GatherArgs {
     int nwarps;          // consumer warps per CTA
     int has_heavy;       // add p.H[owner] before the epilogue
     int KT;              // accumulators per lane = 2 * NL
+    int ready32;         // a warp spends a step when >= live * ready32 / 32 lanes are ready (tunable)
+    int lag_rows;        // ... or when its slowest lane is this far behind the landed edge
     int64_t table_stride;   // doubles per restart of the gather table
     const double* table;
     double* plain_out;   // GM_PLAIN: [n_owner, 16]
@@ -477,61 +481,71 @@ k_gather(const GatherView gv, const EmP p, const GatherArgs ga) {
         if (blk_left) { nx2 = __ldg(sp); sp += 32; --blk_left; }
         int cnt = 4;
         int g = 0, phys = 0;
-        int hi = 0, released = 0;
+        int released = 0;
         const uint32_t qx = (uint32_t)(lane & 7) << 4;
 
+        const int n_gather = (int)gv.n_gather;
+        int landed_seen = -1;
+        const uint32_t prog_addr = smem_u32((const void*)(progress + w));
         for (;;) {
-#pragma unroll 1
-            for (int e = 0; e < VB_G_EPOCH; ++e) {
-                const uint32_t r = cur.x & 0xffffu;
-                const int d = (int)(r >> VB_REC_COUNT_BITS);
-                const int gn = g + d;
-                const bool can = rem != 0 && gn < hi;
-                if (!__any_sync(VB_FULL, can)) break;
-                if (can) {
-                    int pn = phys + d;
-                    pn -= pn >= VB_RING_ROWS ? VB_RING_ROWS : 0;
-                    pn -= pn >= VB_RING_ROWS ? VB_RING_ROWS : 0;
-                    g = gn;
-                    phys = pn;
-                    const uint32_t c = r & VB_REC_MAX_COUNT;
-                    cur.x = __funnelshift_r(cur.x, cur.y, 16);
-                    cur.y >>= 16;
-                    --rem;
-                    if (--cnt == 0) {
-                        cur = nx1;
-                        nx1 = nx2;
-                        if (blk_left) { nx2 = __ldg(sp); sp += 32; --blk_left; }
-                        cnt = 4;
-                    }
-                    if (c) {
-                        const double dm = (double)c;
-                        const unsigned char* row = smem + ((uint32_t)pn << 7);
-#pragma unroll
-                        for (int t = 0; t < NL; ++t) {
-                            const double2 v = *reinterpret_cast<const double2*>(row + (qx ^ (uint32_t)(t << 4)));
-                            acc[2 * t] = fma(dm, v.x, acc[2 * t]);
-                            acc[2 * t + 1] = fma(dm, v.y, acc[2 * t + 1]);
-                        }
-                    }
-                }
-            }
-            // ---- bookkeeping: release slabs every lane has passed, pick up slabs that have landed
-            const int nxt = rem ? g + (int)((cur.x & 0xffffu) >> VB_REC_COUNT_BITS) : 0x7fffffff;
-            const int lo = __reduce_min_sync(VB_FULL, nxt);
+            // slabs that have landed (published by the producer warp), re-read every step: a stale edge
+            // shrinks the usable window of the ring
+            int ld;
+            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ld) : "r"(ring + VB_G_OFF_LANDED) : "memory");
+            const int hi = ld * VB_SLAB_ROWS;
+            const uint32_t r = cur.x & 0xffffu;
+            const int d = (int)(r >> VB_REC_COUNT_BITS);
+            const int gn = g + d;
+            const bool can = rem != 0 && gn < hi;
+            const unsigned ready = __ballot_sync(VB_FULL, can);
+            // release the slabs every lane of this warp has passed
+            const int lo = __reduce_min_sync(VB_FULL, rem ? gn : 0x7fffffff);
             if (lo == 0x7fffffff) break;
             const int rel = lo / VB_SLAB_ROWS;
             if (rel > released) {
                 released = rel;
-                __syncwarp();
-                if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32((const void*)(progress + w))), "r"(rel) : "memory");
+                if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(prog_addr), "r"(rel) : "memory");
             }
-            for (;;) {
-                int ld;
-                asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ld) : "r"(ring + VB_G_OFF_LANDED) : "memory");
-                hi = ld * VB_SLAB_ROWS;
-                if (lo < hi) break;
-                __nanosleep(64);
+            bool go = ready != 0;
+            if (go && ga.ready32 && hi < n_gather) {
+                // optional throttle: a step costs the same issue slots with 4 ready lanes as with 32; wait for
+                // more lanes unless this warp holds the ring back
+                const int live = __popc(__ballot_sync(VB_FULL, rem != 0));
+                if (__popc(ready) < ((live * ga.ready32) >> 5) && hi - lo < ga.lag_rows) go = false;
+            }
+            if (!go) {
+                if (ld == landed_seen) __nanosleep(32);
+                landed_seen = ld;
+                continue;
+            }
+            landed_seen = ld;
+            if (can) {
+                int pn = phys + d;
+                pn -= pn >= VB_RING_ROWS ? VB_RING_ROWS : 0;
+                pn -= pn >= VB_RING_ROWS ? VB_RING_ROWS : 0;
+                g = gn;
+                phys = pn;
+                const uint32_t c = r & VB_REC_MAX_COUNT;
+                cur.x = __funnelshift_r(cur.x, cur.y, 16);
+                cur.y >>= 16;
+                --rem;
+                if (--cnt == 0) {
+                    cur = nx1;
+                    nx1 = nx2;
+                    if (blk_left) { nx2 = __ldg(sp); sp += 32; --blk_left; }
+                    cnt = 4;
+                }
+                if (c) {
+                    const double dm = (double)c;
+                    const uint32_t row = ring + ((uint32_t)pn << 7) + qx;   // ring is 1024-byte aligned
+#pragma unroll
+                    for (int t = 0; t < NL; ++t) {
+                        double vx, vy;
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(row ^ (uint32_t)(t << 4)));
+                        acc[2 * t] = fma(dm, vx, acc[2 * t]);
+                        acc[2 * t + 1] = fma(dm, vy, acc[2 * t + 1]);
+                    }
+                }
             }
         }
         __syncwarp();
@@ -738,6 +752,19 @@ int vb_gather_launch(const vb_counts* m, const EmP& p, int ori, int mode, int th
     ga.table_stride = g.n_gather * VB_ROW_DOUBLES;
     ga.plain_out = plain_out;
     ga.has_heavy = g.n_heavy > 0;
+    {
+        static int ready32 = -1, lag_slabs = -1;
+        if (ready32 < 0) {
+            const char* e = getenv("VIREO_B200_READY32");
+            ready32 = e ? atoi(e) : 0;
+            e = getenv("VIREO_B200_LAG_SLABS");
+            lag_slabs = e ? atoi(e) : VB_RING_SLABS - 3;
+            if (ready32 < 0 || ready32 > 32) ready32 = 0;
+            if (lag_slabs < 1 || lag_slabs > VB_RING_SLABS - 1) lag_slabs = VB_RING_SLABS - 3;
+        }
+        ga.ready32 = ready32;
+        ga.lag_rows = lag_slabs * VB_SLAB_ROWS;
+    }
     int grid_x;
     vb_gather_geometry(m, g, &grid_x, &ga.nwarps);
     const int cls = ori ? 0 : 3;
