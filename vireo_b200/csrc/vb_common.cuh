@@ -39,7 +39,8 @@
 #define VB_SLAB_ROWS 128                  // rows per bulk copy (16 KB)
 #define VB_RING_SLABS 12                  // slabs resident in shared memory (192 KB)
 #define VB_RING_ROWS (VB_SLAB_ROWS * VB_RING_SLABS)
-#define VB_GATHER_MAX_WARPS 22            // consumer warps per CTA (+1 producer warp)
+#define VB_GATHER_MAX_WARPS 24            // consumer warps per CTA (+1 producer warp): 800 threads x 80 registers
+#define VB_SPARSE_LEN 64                  // streams this short may be routed to the residual kernel
 
 struct GatherSet {
     int built;
@@ -56,6 +57,8 @@ struct GatherSet {
     int64_t* hptr;           // [n_owner+1] residual CSR
     int32_t* hrow;
     uint32_t* hcnt;
+    int32_t* cta_start;      // [grid+1] first warp slot of each CTA (contiguous ranges, balanced by records)
+    int grid, max_warps;
     int64_t bytes;
 };
 
@@ -68,6 +71,7 @@ struct GatherView {
     const int64_t* __restrict__ hptr;
     const int32_t* __restrict__ hrow;
     const uint32_t* __restrict__ hcnt;
+    const int32_t* __restrict__ cta_start;
 };
 
 struct vb_counts {

@@ -23,6 +23,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "vb_common.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -90,6 +92,20 @@ __global__ void k_gs_count(const CountsView m, int64_t n_owner, uint32_t* __rest
     }
 }
 
+// owners routed to the residual kernel entirely (sorted ranks >= first_sparse): their stream is empty
+__global__ void k_gs_mark_sparse(const int32_t* __restrict__ perm_sorted, int64_t first_sparse, int64_t n_owner,
+                                 uint8_t* __restrict__ sparse, uint32_t* __restrict__ len_sorted, uint32_t* __restrict__ len,
+                                 uint32_t* __restrict__ n_light, uint32_t* __restrict__ n_heavy) {
+    for (int64_t r = first_sparse + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_owner; r += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t o = perm_sorted[r];
+        sparse[o] = 1;
+        len_sorted[r] = 0;
+        len[o] = 0;
+        n_heavy[o] += n_light[o];
+        n_light[o] = 0;
+    }
+}
+
 __global__ void k_gs_iota(int32_t* out, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = (int32_t)i;
@@ -105,17 +121,19 @@ __global__ void k_gs_slot_blocks(const uint32_t* __restrict__ len_sorted, int64_
 template <int ORI, bool WIDE>
 __global__ void k_gs_fill(const CountsView m, int64_t n_pos, const int32_t* __restrict__ perm,
                           const uint32_t* __restrict__ slot_blk, uint16_t* __restrict__ rec,
-                          const int64_t* __restrict__ hptr, int32_t* __restrict__ hrow, uint32_t* __restrict__ hcnt) {
+                          const int64_t* __restrict__ hptr, int32_t* __restrict__ hrow, uint32_t* __restrict__ hcnt,
+                          const uint8_t* __restrict__ sparse) {
     for (int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pos < n_pos; pos += (int64_t)gridDim.x * blockDim.x) {
         const int64_t o = perm[pos];
         if (o < 0) continue;
+        const bool all_residual = sparse[o] != 0;
         const int lane = (int)(pos & 31);
         uint16_t* base = rec + (size_t)slot_blk[pos >> 5] * 128 + lane * 4;
         uint32_t t = 0;
         int prev = 0;
         int64_t h = hptr[o];
         for_records<ORI, WIDE>(m, o, [&](int g, uint32_t c) {
-            if (c > VB_REC_MAX_COUNT) { hrow[h] = g; hcnt[h] = c; ++h; return; }
+            if (c > VB_REC_MAX_COUNT || all_residual) { hrow[h] = g; hcnt[h] = c; ++h; return; }
             int d = g - prev;
             while (d > VB_REC_MAX_DELTA) {
                 base[(size_t)(t >> 2) * 128 + (t & 3)] = (uint16_t)(VB_REC_MAX_DELTA << VB_REC_COUNT_BITS);
@@ -172,7 +190,7 @@ struct GsScratch {
 
 static void gather_set_free(GatherSet& g) {
     cudaFree(g.perm); cudaFree(g.len); cudaFree(g.slot_blk); cudaFree(g.rec);
-    cudaFree(g.hptr); cudaFree(g.hrow); cudaFree(g.hcnt);
+    cudaFree(g.hptr); cudaFree(g.hrow); cudaFree(g.hcnt); cudaFree(g.cta_start);
     memset(&g, 0, sizeof(g));
 }
 
@@ -190,7 +208,7 @@ static int build_one(vb_counts* m, GatherSet& g, cudaStream_t st) {
     const int sm = m->sm_count;
     const int64_t O = ORI == 0 ? m->C : 2 * m->V;
     const int64_t Gn = ORI == 0 ? 2 * m->V : m->C;
-    if (O >= (1ll << 31) - 64 || Gn >= (1ll << 31) - 64) { vb_set_error("gather format: more than 2^31 rows"); return VB_E_UNSUPPORTED; }
+    if (O >= (1ll << 31) - 64 || Gn >= (1ll << 23)) { vb_set_error("gather format: more than 2^31 owner rows or 2^23 gather rows"); return VB_E_UNSUPPORTED; }
     const int64_t n_slot = (O + 31) / 32;
     const int64_t n_pos = n_slot * 32;
     const CountsView v = gs_view(m);
@@ -230,6 +248,10 @@ static int build_one(vb_counts* m, GatherSet& g, cudaStream_t st) {
     VB_CUDA(cudaMalloc(&g.len, (n_pos ? n_pos : 1) * sizeof(uint32_t)));
     VB_CUDA(cudaMalloc(&g.slot_blk, (n_slot + 1) * sizeof(uint32_t)));
     VB_CUDA(cudaMemsetAsync(g.perm, 0xff, (n_pos ? n_pos : 1) * sizeof(int32_t), st));
+    uint8_t* sparse;
+    if ((rc = tmp.alloc(&sparse, O))) return rc;
+    VB_CUDA(cudaMemsetAsync(sparse, 0, O ? O : 1, st));
+    std::vector<uint32_t> hlen((size_t)n_pos, 0u);
     if (O) {
         size_t tb = 0;
         VB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, len, len_sorted, ids, perm_sorted, O, 0, 32, st));
@@ -237,8 +259,68 @@ static int build_one(vb_counts* m, GatherSet& g, cudaStream_t st) {
         if ((rc = tmp.alloc((unsigned char**)&cub_tmp, tb))) return rc;
         VB_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_tmp, tb, len, len_sorted, ids, perm_sorted, O, 0, 32, st));
         VB_CUDA(cudaMemcpyAsync(g.perm, perm_sorted, O * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        VB_CUDA(cudaMemcpyAsync(hlen.data(), len_sorted, O * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        // Owners with a short stream ride the front edge of the ring and spend a whole warp step on one or two
+        // records; when such owners carry a negligible share of the records (e.g. the alternative-allele rows of
+        // homozygous-reference SNPs) their pairs go to the residual kernel instead.
+        int64_t first_sparse = O, moved = 0;
+        const int64_t budget = g.n_rec / 50;
+        while (first_sparse > 0 && hlen[first_sparse - 1] <= VB_SPARSE_LEN && moved + hlen[first_sparse - 1] <= budget) {
+            moved += hlen[first_sparse - 1];
+            --first_sparse;
+        }
+        while (first_sparse < O && hlen[first_sparse] == 0) ++first_sparse;   // nothing to move for empty streams
+        if (moved > 0) {
+            k_gs_mark_sparse<<<grid1d(O - first_sparse, sm), 256, 0, st>>>(perm_sorted, first_sparse, O, sparse, len_sorted, len, nl, nh);
+            VB_CUDA(cudaGetLastError());
+            for (int64_t r = first_sparse; r < O; ++r) hlen[r] = 0;
+            VB_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(unsigned long long), st));
+            k_gs_sum3<<<grid1d(O, sm), 256, 0, st>>>(len, nl, nh, O, sums);
+            VB_CUDA(cudaGetLastError());
+            VB_CUDA(cudaMemcpyAsync(hsums, sums, sizeof(hsums), cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaStreamSynchronize(st));
+            g.n_rec = (int64_t)hsums[0]; g.n_light = (int64_t)hsums[1]; g.n_heavy = (int64_t)hsums[2];
+        }
     }
     VB_CUDA(cudaMemcpyAsync(g.len, len_sorted, (n_pos ? n_pos : 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    {
+        // Warp slots are dealt alternately from the long and the short end of the sorted list (position p ->
+        // slot p/2 or n_slot-1-p/2), and a CTA is a contiguous range of positions sized so that every CTA
+        // carries about the same number of records with at most VB_GATHER_MAX_WARPS slots.  Mixing both ends
+        // keeps bimodal length distributions (reference- vs alternative-allele rows) within the slot limit.
+        std::vector<int32_t> start;
+        start.push_back(0);
+        const double target = (double)g.n_rec / (double)sm;
+        double acc_rec = 0.0, done_rec = 0.0;
+        int in_cta = 0;
+        for (int64_t s = 0; s < n_slot; ++s) {
+            double r = 0.0;
+            const int64_t sl = (s & 1) ? n_slot - 1 - (s >> 1) : (s >> 1);
+            for (int l = 0; l < 32; ++l) r += hlen[(size_t)sl * 32 + l];
+            const int64_t ctas = (int64_t)start.size();                 // CTAs opened so far (incl. the current one)
+            const bool full = in_cta >= VB_GATHER_MAX_WARPS;
+            // close the current CTA when adding this slot would overshoot its share of what is left
+            const bool share = in_cta > 0 && target > 0.0 && ctas < sm && acc_rec + 0.5 * r > (double)ctas * target - done_rec;
+            if (full || share) {
+                start.push_back((int32_t)s);
+                done_rec += acc_rec;
+                acc_rec = 0.0;
+                in_cta = 0;
+            }
+            acc_rec += r;
+            ++in_cta;
+        }
+        start.push_back((int32_t)n_slot);
+        if (n_slot == 0) { start.clear(); start.push_back(0); start.push_back(0); }
+        g.grid = (int)start.size() - 1;
+        g.max_warps = 1;
+        for (size_t i = 0; i + 1 < start.size(); ++i)
+            if (start[i + 1] - start[i] > g.max_warps) g.max_warps = start[i + 1] - start[i];
+        VB_CUDA(cudaMalloc(&g.cta_start, start.size() * sizeof(int32_t)));
+        VB_CUDA(cudaMemcpyAsync(g.cta_start, start.data(), start.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+    }
     k_gs_slot_blocks<<<grid1d(n_slot + 1, sm), 256, 0, st>>>(len_sorted, n_slot, nblk);
     VB_CUDA(cudaGetLastError());
     {
@@ -273,8 +355,8 @@ static int build_one(vb_counts* m, GatherSet& g, cudaStream_t st) {
     VB_CUDA(cudaMalloc(&g.rec, ((size_t)total_blk * 128 + 64) * sizeof(uint16_t)));
     VB_CUDA(cudaMemsetAsync(g.rec, 0, ((size_t)total_blk * 128 + 64) * sizeof(uint16_t), st));
     if (O) {
-        if (m->wide) k_gs_fill<ORI, true><<<grid1d(n_pos, sm), 256, 0, st>>>(v, n_pos, g.perm, g.slot_blk, g.rec, g.hptr, g.hrow, g.hcnt);
-        else k_gs_fill<ORI, false><<<grid1d(n_pos, sm), 256, 0, st>>>(v, n_pos, g.perm, g.slot_blk, g.rec, g.hptr, g.hrow, g.hcnt);
+        if (m->wide) k_gs_fill<ORI, true><<<grid1d(n_pos, sm), 256, 0, st>>>(v, n_pos, g.perm, g.slot_blk, g.rec, g.hptr, g.hrow, g.hcnt, sparse);
+        else k_gs_fill<ORI, false><<<grid1d(n_pos, sm), 256, 0, st>>>(v, n_pos, g.perm, g.slot_blk, g.rec, g.hptr, g.hrow, g.hcnt, sparse);
         VB_CUDA(cudaGetLastError());
     }
     VB_CUDA(cudaStreamSynchronize(st));
@@ -371,8 +453,8 @@ k_pad_rows(const double* __restrict__ src, int64_t n_row, int K, int KT, double*
 // ---------------------------------------------------------------------------------------------
 // k_gather
 // ---------------------------------------------------------------------------------------------
-#define VB_G_EPOCH 8
-#define VB_G_LAG_ROWS ((VB_RING_SLABS - 3) * VB_SLAB_ROWS)
+#define VB_G_EPOCH 4
+#define VB_G_RING_MAGIC ((uint32_t)((0x100000000ull + VB_RING_ROWS - 1) / VB_RING_ROWS))
 #define VB_G_RING_BYTES (VB_RING_ROWS * VB_ROW_DOUBLES * 8)
 #define VB_G_SLAB_BYTES (VB_SLAB_ROWS * VB_ROW_DOUBLES * 8)
 #define VB_G_RED_DOUBLES (2 * VB_MAX_GT)
@@ -386,11 +468,9 @@ k_pad_rows(const double* __restrict__ src, int64_t n_row, int K, int KT, double*
 struct GatherArgs {
     int mode;            // GM_*
     int theta_mode;      // GM_SNP: 0 never, 1 always, 2 per the device iteration counter
-    int nwarps;          // consumer warps per CTA
+    int nwarps;          // largest number of consumer warps of a CTA (block size = (nwarps + 1) * 32)
     int has_heavy;       // add p.H[owner] before the epilogue
     int KT;              // accumulators per lane = 2 * NL
-    int ready32;         // a warp spends a step when >= live * ready32 / 32 lanes are ready (tunable)
-    int lag_rows;        // ... or when its slowest lane is this far behind the landed edge
     int64_t table_stride;   // doubles per restart of the gather table
     const double* table;
     double* plain_out;   // GM_PLAIN: [n_owner, 16]
@@ -406,7 +486,8 @@ k_gather(const GatherView gv, const EmP p, const GatherArgs ga) {
     if (ga.mode == GM_SNP && !p.bmm && !do_theta && !p.learn_gt && ga.theta_mode == 2) return;   // S1/S2 unused this iteration
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int nwarps = ga.nwarps;
+    const int slot0 = gv.cta_start[blockIdx.x];
+    const int nwarps = gv.cta_start[blockIdx.x + 1] - slot0;      // consumer warps of this CTA; warp `nwarps` produces
     const uint32_t ring = smem_u32(smem);
     const uint32_t bars = ring + VB_G_OFF_BAR;
     volatile int* progress = reinterpret_cast<volatile int*>(smem + VB_G_OFF_PROG);
@@ -466,90 +547,75 @@ k_gather(const GatherView gv, const EmP p, const GatherArgs ga) {
         }
     } else if (w < nwarps) {
         // ---------------- consumer warp: one owner per lane
-        const int64_t slot = (int64_t)blockIdx.x + (int64_t)w * gridDim.x;
+        const int64_t pos = (int64_t)slot0 + w;       // dealing position -> warp slot (long and short ends alternate)
+        const int64_t slot = (pos & 1) ? gv.n_slot - 1 - (pos >> 1) : (pos >> 1);
         uint32_t rem = 0;
-        const uint2* sp = nullptr;
-        if (slot < gv.n_slot) {
+        const uint2* sp = reinterpret_cast<const uint2*>(gv.rec);
+        {
             owner = gv.perm[slot * 32 + lane];
             rem = gv.len[slot * 32 + lane];
-            sp = reinterpret_cast<const uint2*>(gv.rec) + (size_t)gv.slot_blk[slot] * 32 + lane;
+            sp += (size_t)gv.slot_blk[slot] * 32 + lane;
         }
-        uint32_t blk_left = (rem + 3u) >> 2;
-        uint2 cur = make_uint2(0, 0), nx1 = cur, nx2 = cur;
+        uint32_t blk_left = (rem + 3u) >> 2;       // 4 records per 8-byte block; one block is prefetched ahead
+        uint2 cur = make_uint2(0, 0), nxt = cur;
         if (blk_left) { cur = __ldg(sp); sp += 32; --blk_left; }
-        if (blk_left) { nx1 = __ldg(sp); sp += 32; --blk_left; }
-        if (blk_left) { nx2 = __ldg(sp); sp += 32; --blk_left; }
-        int cnt = 4;
-        int g = 0, phys = 0;
-        int released = 0;
-        const uint32_t qx = (uint32_t)(lane & 7) << 4;
-
-        const int n_gather = (int)gv.n_gather;
-        int landed_seen = -1;
+        if (blk_left) { nxt = __ldg(sp); sp += 32; --blk_left; }
+        uint32_t phase = 4;                        // records left in `cur`
+        int g = 0;                                 // gather row of the last consumed record
+        int released = 0, landed_seen = -1;
+        const uint32_t lane_base = ring + ((uint32_t)(lane & 7) << 4);   // ring is 1024-byte aligned
         const uint32_t prog_addr = smem_u32((const void*)(progress + w));
         for (;;) {
-            // slabs that have landed (published by the producer warp), re-read every step: a stale edge
-            // shrinks the usable window of the ring
+            // ---- bookkeeping, once per VB_G_EPOCH steps: landed edge, slabs every lane has passed
             int ld;
             asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ld) : "r"(ring + VB_G_OFF_LANDED) : "memory");
             const int hi = ld * VB_SLAB_ROWS;
-            const uint32_t r = cur.x & 0xffffu;
-            const int d = (int)(r >> VB_REC_COUNT_BITS);
-            const int gn = g + d;
-            const bool can = rem != 0 && gn < hi;
-            const unsigned ready = __ballot_sync(VB_FULL, can);
-            // release the slabs every lane of this warp has passed
-            const int lo = __reduce_min_sync(VB_FULL, rem ? gn : 0x7fffffff);
+            const int lo = __reduce_min_sync(VB_FULL, rem ? g + (int)((cur.x & 0xffffu) >> VB_REC_COUNT_BITS) : 0x7fffffff);
             if (lo == 0x7fffffff) break;
             const int rel = lo / VB_SLAB_ROWS;
             if (rel > released) {
                 released = rel;
                 if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(prog_addr), "r"(rel) : "memory");
             }
-            bool go = ready != 0;
-            if (go && ga.ready32 && hi < n_gather) {
-                // optional throttle: a step costs the same issue slots with 4 ready lanes as with 32; wait for
-                // more lanes unless this warp holds the ring back
-                const int live = __popc(__ballot_sync(VB_FULL, rem != 0));
-                if (__popc(ready) < ((live * ga.ready32) >> 5) && hi - lo < ga.lag_rows) go = false;
-            }
-            if (!go) {
+            if (lo >= hi) {                        // every lane waits for a slab that has not landed
                 if (ld == landed_seen) __nanosleep(32);
                 landed_seen = ld;
                 continue;
             }
             landed_seen = ld;
-            if (can) {
-                int pn = phys + d;
-                pn -= pn >= VB_RING_ROWS ? VB_RING_ROWS : 0;
-                pn -= pn >= VB_RING_ROWS ? VB_RING_ROWS : 0;
-                g = gn;
-                phys = pn;
-                const uint32_t c = r & VB_REC_MAX_COUNT;
-                cur.x = __funnelshift_r(cur.x, cur.y, 16);
-                cur.y >>= 16;
-                --rem;
-                if (--cnt == 0) {
-                    cur = nx1;
-                    nx1 = nx2;
-                    if (blk_left) { nx2 = __ldg(sp); sp += 32; --blk_left; }
-                    cnt = 4;
-                }
-                if (c) {
-                    const double dm = (double)c;
-                    const uint32_t row = ring + ((uint32_t)pn << 7) + qx;   // ring is 1024-byte aligned
 #pragma unroll
-                    for (int t = 0; t < NL; ++t) {
-                        double vx, vy;
-                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(row ^ (uint32_t)(t << 4)));
-                        acc[2 * t] = fma(dm, vx, acc[2 * t]);
-                        acc[2 * t + 1] = fma(dm, vy, acc[2 * t + 1]);
+            for (int e = 0; e < VB_G_EPOCH; ++e) {
+                const uint32_t r = cur.x & 0xffffu;
+                const int gn = g + (int)(r >> VB_REC_COUNT_BITS);
+                if (rem != 0 && gn < hi) {
+                    g = gn;
+                    const uint32_t c = r & VB_REC_MAX_COUNT;
+                    cur.x = __funnelshift_r(cur.x, cur.y, 16);
+                    cur.y >>= 16;
+                    --rem;
+                    if (--phase == 0) {
+                        cur = nxt;
+                        phase = 4;
+                        if (blk_left) { nxt = __ldg(sp); sp += 32; --blk_left; }
+                    }
+                    if (c) {
+                        const double dm = (double)c;
+                        // ring position of row gn: gn mod VB_RING_ROWS by multiply-shift (exact for gn < 2^23)
+                        const uint32_t q1536 = __umulhi((uint32_t)gn, VB_G_RING_MAGIC);
+                        const uint32_t row = lane_base + (((uint32_t)gn - q1536 * VB_RING_ROWS) << 7);
+#pragma unroll
+                        for (int t = 0; t < NL; ++t) {
+                            double vx, vy;
+                            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(row ^ (uint32_t)(t << 4)));
+                            acc[2 * t] = fma(dm, vx, acc[2 * t]);
+                            acc[2 * t + 1] = fma(dm, vy, acc[2 * t + 1]);
+                        }
                     }
                 }
             }
         }
         __syncwarp();
-        if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32((const void*)(progress + w))), "r"(0x7fffffff) : "memory");
+        if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(prog_addr), "r"(0x7fffffff) : "memory");
     }
 
     // ---------------- epilogue: lane-local, K values per owner
@@ -704,16 +770,9 @@ k_gather(const GatherView gv, const EmP p, const GatherArgs ga) {
 // host: launch geometry and dispatch
 // ---------------------------------------------------------------------------------------------
 void vb_gather_geometry(const vb_counts* m, const GatherSet& g, int* grid, int* nwarps) {
-    const int64_t per_wave = (int64_t)m->sm_count * VB_GATHER_MAX_WARPS;
-    int64_t waves = (g.n_slot + per_wave - 1) / per_wave;
-    if (waves < 1) waves = 1;
-    int64_t gr = (int64_t)m->sm_count * waves;
-    if (gr > g.n_slot) gr = g.n_slot;
-    if (gr < 1) gr = 1;
-    *grid = (int)gr;
-    int64_t nw = (g.n_slot + gr - 1) / gr;
-    if (nw < 1) nw = 1;
-    *nwarps = (int)nw;
+    (void)m;
+    *grid = g.grid > 0 ? g.grid : 1;
+    *nwarps = g.max_warps > 0 ? g.max_warps : 1;
 }
 
 static bool g_attr_set = false;
@@ -728,7 +787,7 @@ static GatherView view_of_set(const GatherSet& g) {
     GatherView v;
     v.n_owner = g.n_owner; v.n_gather = g.n_gather; v.n_slot = g.n_slot;
     v.perm = g.perm; v.len = g.len; v.slot_blk = g.slot_blk; v.rec = g.rec;
-    v.hptr = g.hptr; v.hrow = g.hrow; v.hcnt = g.hcnt;
+    v.hptr = g.hptr; v.hrow = g.hrow; v.hcnt = g.hcnt; v.cta_start = g.cta_start;
     return v;
 }
 
@@ -752,19 +811,6 @@ int vb_gather_launch(const vb_counts* m, const EmP& p, int ori, int mode, int th
     ga.table_stride = g.n_gather * VB_ROW_DOUBLES;
     ga.plain_out = plain_out;
     ga.has_heavy = g.n_heavy > 0;
-    {
-        static int ready32 = -1, lag_slabs = -1;
-        if (ready32 < 0) {
-            const char* e = getenv("VIREO_B200_READY32");
-            ready32 = e ? atoi(e) : 0;
-            e = getenv("VIREO_B200_LAG_SLABS");
-            lag_slabs = e ? atoi(e) : VB_RING_SLABS - 3;
-            if (ready32 < 0 || ready32 > 32) ready32 = 0;
-            if (lag_slabs < 1 || lag_slabs > VB_RING_SLABS - 1) lag_slabs = VB_RING_SLABS - 3;
-        }
-        ga.ready32 = ready32;
-        ga.lag_rows = lag_slabs * VB_SLAB_ROWS;
-    }
     int grid_x;
     vb_gather_geometry(m, g, &grid_x, &ga.nwarps);
     const int cls = ori ? 0 : 3;
