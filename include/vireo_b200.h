@@ -128,6 +128,12 @@ typedef struct vb_vireo_args {
 
 int vb_vireo_ws_sizes(const vb_counts* m, int n_donor, int n_gt, int n_batch, int ase_mode, vb_ws_sizes* out);
 
+/* Priors enter the kernels as logs, in two flavours: log(prior) as the softmax adds it
+ * (vireoSNP/utils/vireo_model.py:198,218; bmm_model.py:153) and the log of the row-normalised prior that
+ * scipy.stats.entropy compares against (vireo_model.py:237-238; bmm_model.py:166).  prior, log_raw, log_norm:
+ * device arrays [n_row, n_col], rows normalised over n_col. */
+int vb_log_prior(const double* prior, int64_t n_row, int n_col, double* log_raw, double* log_norm, void* stream);
+
 /* Run the coordinate-ascent loop of Vireo._fit_VB (vireoSNP/utils/vireo_model.py:251-276) for a batch
  * of restarts entirely on the device: per iteration update_theta_size (:165-185), update_GT_prob
  * (:204-219), update_ID_prob (:187-201) and get_ELBO (:222-248), with the reference's convergence

@@ -209,13 +209,37 @@ def _ptr(tensor):
     return C.c_void_p(tensor.data_ptr())
 
 
-def _log_prior_pair(prior):
-    """(log prior as used inside the softmax, log of the row-normalised prior as scipy.stats.entropy uses)."""
-    prior = np.asarray(prior, dtype=np.float64)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        raw = np.log(prior)
-        norm = np.log(prior / prior.sum(axis=-1, keepdims=True))
+def _log_prior_pair(prior, device):
+    """Device tensors (log prior as used inside the softmax, log of the row-normalised prior as
+    scipy.stats.entropy uses); the prior is uploaded once and both logs are taken by a kernel."""
+    prior = np.ascontiguousarray(prior, dtype=np.float64)
+    n_col = prior.shape[-1]
+    n_row = prior.size // max(n_col, 1)
+    src = _dev(prior.reshape(-1), device)
+    raw, norm = _zeros(prior.size, device), _zeros(prior.size, device)
+    with torch().cuda.device(device):
+        _lib.check(_lib.load().vb_log_prior(_ptr(src), n_row, n_col, _ptr(raw), _ptr(norm), _stream(device)))
     return raw, norm
+
+
+_PINNED = {}
+
+
+def _to_host(tensor):
+    """Device tensor -> fresh numpy array, through a reused pinned staging buffer (pageable
+    device-to-host copies run at a fraction of the link rate)."""
+    t = torch()
+    n = tensor.numel()
+    key = (n, tensor.dtype)
+    buf = _PINNED.get(key)
+    if buf is None:
+        if len(_PINNED) > 16:
+            _PINNED.clear()
+        buf = t.empty(n, dtype=tensor.dtype, pin_memory=True)
+        _PINNED[key] = buf
+    buf.copy_(tensor.reshape(-1), non_blocking=True)
+    t.cuda.current_stream(tensor.device).synchronize()
+    return buf.numpy().copy().reshape(tuple(tensor.shape))
 
 
 def _compress_rows(a):
@@ -291,13 +315,10 @@ class VireoBatch:
         id_prior = _compress_rows(id_prior)
         if id_prior.shape[0] not in (1, C_) or id_prior.shape[1] != K:
             raise ValueError("ID_prior shape %r does not broadcast to (%d, %d)" % (id_prior.shape, C_, K))
-        raw, norm = _log_prior_pair(id_prior)
         self.id_rows = id_prior.shape[0]
-        self.lidp, self.lidp_kl = _dev(raw, dev), _dev(norm, dev)
+        self.lidp, self.lidp_kl = _log_prior_pair(id_prior, dev)
         gt_prior = np.broadcast_to(np.asarray(m0.GT_prior, dtype=np.float64), (V, K, G))
-        raw, norm = _log_prior_pair(gt_prior)
-        self.lgtp = _dev(raw, dev)
-        self.lgtp_kl = self.lgtp if np.array_equal(raw, norm) else _dev(norm, dev)
+        self.lgtp, self.lgtp_kl = _log_prior_pair(gt_prior, dev)
         s1p = np.asarray(m0.theta_s1_prior, dtype=np.float64).reshape(-1, G)
         s2p = np.asarray(m0.theta_s2_prior, dtype=np.float64).reshape(-1, G)
         if s1p.shape[0] not in (1, T):
@@ -361,13 +382,14 @@ class VireoBatch:
 
     def download(self, what=("ID_prob", "GT_prob", "theta")):
         host = {}
+        B, C_, V, K, G, T = self.B, self.C, self.V, self.K, self.G, self.T
         if "ID_prob" in what:
-            host["ID_prob"] = self.id_prob.cpu().numpy()
+            host["ID_prob"] = _to_host(self.id_prob).reshape(B, C_, K)
         if "GT_prob" in what:
-            host["GT_prob"] = self.gt_prob.cpu().numpy()
+            host["GT_prob"] = _to_host(self.gt_prob).reshape(B, V, K, G)
         if "theta" in what:
-            host["beta_mu"] = self.beta_mu.cpu().numpy()
-            host["beta_sum"] = self.beta_sum.cpu().numpy()
+            host["beta_mu"] = _to_host(self.beta_mu).reshape(B, T, G)
+            host["beta_sum"] = _to_host(self.beta_sum).reshape(B, T, G)
         for b, m in enumerate(self.models):
             if "ID_prob" in host:
                 m.ID_prob = host["ID_prob"][b].copy() if self.B > 1 else host["ID_prob"][b]
@@ -433,9 +455,8 @@ class BmmBatch:
         if id_prior.ndim == 1:
             id_prior = id_prior[None, :]
         id_prior = _compress_rows(id_prior)
-        raw, norm = _log_prior_pair(id_prior)
         self.id_rows = id_prior.shape[0]
-        self.lidp, self.lidp_kl = _dev(raw, dev), _dev(norm, dev)
+        self.lidp, self.lidp_kl = _log_prior_pair(id_prior, dev)
         self.s1p = _dev(np.broadcast_to(np.asarray(model.theta_s1_prior, dtype=np.float64), (V, K)), dev)
         self.s2p = _dev(np.broadcast_to(np.asarray(model.theta_s2_prior, dtype=np.float64), (V, K)), dev)
         ws = _lib.WsSizes()

@@ -58,6 +58,7 @@ SIGNATURES = {
     "vb_counts_info": (C.c_int64, [C.c_void_p, C.c_int]),
     "vb_binom_const": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "vb_vireo_ws_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(WsSizes)]),
+    "vb_log_prior": (C.c_int, [c_dp, C.c_int64, C.c_int, c_dp, c_dp, C.c_void_p]),
     "vb_vireo_fit": (C.c_int, [C.c_void_p, C.POINTER(VireoArgs), C.c_void_p]),
     "vb_vireo_step": (C.c_int, [C.c_void_p, C.POINTER(VireoArgs), C.c_int, C.c_void_p]),
     "vb_bmm_ws_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(WsSizes)]),

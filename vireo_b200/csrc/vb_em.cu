@@ -537,6 +537,23 @@ __global__ void __launch_bounds__(VB_THREADS) k_terms(const EmP p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_log_prior: log(prior) as used inside the softmax (vireo_model.py:198,218) and log of the
+// row-normalised prior as scipy.stats.entropy sees it (:237-238); one thread per row
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VB_THREADS) k_log_prior(const double* __restrict__ prior, int64_t n_row, int n_col,
+                                                          double* __restrict__ log_raw, double* __restrict__ log_norm) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_row; r += (int64_t)gridDim.x * blockDim.x) {
+        const double* p = prior + r * n_col;
+        double s = 0.0;
+        for (int c = 0; c < n_col; ++c) s += p[c];
+        for (int c = 0; c < n_col; ++c) {
+            log_raw[r * n_col + c] = log(p[c]);
+            log_norm[r * n_col + c] = log(p[c] / s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_elbo: final sums + the convergence rule.  advance = 1 inside the fit loop.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_elbo(const EmP p, const int advance) {
@@ -940,6 +957,17 @@ static int run_loop(const vb_counts* m, const EmP& p, int poll_every, cudaStream
             if (done) break;
         }
     }
+    return VB_OK;
+}
+
+extern "C" int vb_log_prior(const double* prior, int64_t n_row, int n_col, double* log_raw, double* log_norm, void* stream) {
+    if (!prior || !log_raw || !log_norm || n_row < 0 || n_col < 1) { vb_set_error("bad argument"); return VB_E_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t nb = (n_row + VB_THREADS - 1) / VB_THREADS;
+    if (nb > 148 * 8) nb = 148 * 8;
+    if (nb < 1) nb = 1;
+    VB_LAUNCH(7, st, k_log_prior<<<(unsigned)nb, VB_THREADS, 0, st>>>(prior, n_row, n_col, log_raw, log_norm));
+    VB_CUDA(cudaGetLastError());
     return VB_OK;
 }
 
