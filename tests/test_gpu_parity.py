@@ -32,15 +32,31 @@ def vb():
     return vireo_b200
 
 
-@pytest.fixture(autouse=True, params=["rows", "gather"])
+CURRENT_PATH = ["auto"]
+
+
+@pytest.fixture(autouse=True, params=["rows", "gather", "seg", "seg32"])
 def kernel_path(request):
-    """Every parity test runs against both kernel families of the two sparse passes: the row kernels
-    (one warp per row, L2 gathers) and the gather-stream kernels (lane per row, table streamed through
-    shared memory by bulk async copies).  In production the choice is automatic (vb_set_path(0))."""
+    """Every parity test runs against every kernel family of the two sparse passes: the row kernels
+    (one warp per row, L2 gathers), the gather-stream kernels (lane per row, table streamed through
+    shared memory by bulk async copies), and the window-segment kernels (lane group per row, table
+    windows in shared memory) with FP64 tables ("seg") and with 32-bit fixed-point tables and exact
+    integer accumulation ("seg32"; Vireo without ASE mode, other models use the FP64 tables).
+    In production the choice is automatic (vb_set_path(0))."""
     from vireo_b200 import _lib
     _lib.set_path(request.param)
+    CURRENT_PATH[0] = request.param
     yield request.param
+    CURRENT_PATH[0] = "auto"
     _lib.set_path("auto")
+
+
+def _tight(tol):
+    """Tolerance of a teacher-forced single update.  The fixed-point tables of "seg32" carry a quantisation
+    error of at most reads_per_row * 2^-33 * table range on every log-likelihood (about 1e-6 worst case,
+    1e-8 typical on the fixtures), far inside the 1e-5 north-star gate but above the FP64 round-off
+    the other families are held to."""
+    return max(tol, 2e-6) if CURRENT_PATH[0] == "seg32" else tol
 
 
 def _quiet(fn, *a, **k):
@@ -142,12 +158,12 @@ def test_single_updates_teacher_forced(vb, cellsnp):
     rel_close(m.beta_mu, z["beta_mu1"], 1e-12, "beta_mu")
     rel_close(m.beta_sum, z["beta_sum1"], 1e-12, "beta_sum")
     m.update_GT_prob(AD, DP)
-    rel_close(m.GT_prob, z["GT_prob2"], 1e-9, "GT_prob")
+    rel_close(m.GT_prob, z["GT_prob2"], _tight(1e-9), "GT_prob")
     ll = m.update_ID_prob(AD, DP)
-    assert np.max(np.abs(ll - z["logLik_ID3"])) < 1e-9
-    rel_close(m.ID_prob, z["ID_prob3"], 1e-9, "ID_prob")
-    assert abs(m.get_ELBO(ll) - float(z["ELBO3"])) <= 1e-9 * abs(float(z["ELBO3"]))
-    assert abs(m.get_ELBO(None, AD, DP) - float(z["ELBO3_none"])) <= 1e-9 * abs(float(z["ELBO3_none"]))
+    assert np.max(np.abs(ll - z["logLik_ID3"])) < _tight(1e-9)
+    rel_close(m.ID_prob, z["ID_prob3"], _tight(1e-9), "ID_prob")
+    assert abs(m.get_ELBO(ll) - float(z["ELBO3"])) <= _tight(1e-9) * abs(float(z["ELBO3"]))
+    assert abs(m.get_ELBO(None, AD, DP) - float(z["ELBO3_none"])) <= _tight(1e-9) * abs(float(z["ELBO3_none"]))
 
 
 def test_binom_const(vb, cellsnp, mito):
@@ -464,6 +480,6 @@ def test_full_size_invariants(vb, shape):
     ADr, DPr = AD.tocsr(), DP.tocsr()
     ll_lo = lo.update_ID_prob(ADr[:half].tocsc(), DPr[:half].tocsc())
     ll_hi = hi.update_ID_prob(ADr[half:].tocsc(), DPr[half:].tocsc())
-    assert np.max(np.abs(ll_all - (ll_lo + ll_hi))) <= 1e-9 * np.max(np.abs(ll_all))
+    assert np.max(np.abs(ll_all - (ll_lo + ll_hi))) <= _tight(1e-9) * np.max(np.abs(ll_all))
     del mask
     vb.clear_cache()

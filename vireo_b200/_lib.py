@@ -79,6 +79,7 @@ SIGNATURES = {
 }
 
 _lib = None
+PATHS = {"auto": 0, "rows": 1, "gather": 2, "seg": 3, "seg32": 4}
 
 
 class VireoB200Error(RuntimeError):
@@ -100,13 +101,13 @@ def load():
         fn.argtypes = args
     _lib = lib
     env = os.environ.get("VIREO_B200_PATH", "auto").lower()
-    lib.vb_set_path({"auto": 0, "rows": 1, "gather": 2}.get(env, 0))
+    lib.vb_set_path(PATHS.get(env, 0))
     return lib
 
 
 def set_path(mode):
-    """'auto' | 'rows' | 'gather': kernel family of the two sparse passes (see vb_set_path)."""
-    load().vb_set_path({"auto": 0, "rows": 1, "gather": 2}[mode])
+    """'auto' | 'rows' | 'gather' | 'seg' | 'seg32': kernel family of the two sparse passes (see vb_set_path)."""
+    load().vb_set_path(PATHS[mode])
 
 
 KERNEL_CLASSES = ("k_snp", "k_theta", "k_gt", "k_cell", "k_elbo", "k_bmm_theta", "k_terms", "doublet")

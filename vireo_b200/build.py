@@ -11,8 +11,8 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("vb_stage.cu", "vb_em.cu", "vb_gather.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", "vb_common.cuh"),
+SRC = [os.path.join(HERE, "csrc", f) for f in ("vb_stage.cu", "vb_em.cu", "vb_gather.cu", "vb_seg.cu")]
+DEPS = SRC + [os.path.join(HERE, "csrc", "vb_common.cuh"), os.path.join(HERE, "csrc", "vb_stream.cuh"),
               os.path.join(os.path.dirname(HERE), "include", "vireo_b200.h")]
 LIB = os.path.join(HERE, "libvireo_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

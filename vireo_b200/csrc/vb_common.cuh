@@ -74,6 +74,59 @@ struct GatherView {
     const int32_t* __restrict__ cta_start;
 };
 
+
+// ----------------------------------------------------------------------------------------------
+// Window-segment format (vb_seg.cu), one per pass orientation and table precision.
+//   Same (owner, gather row, count) pairs as above.  The gather table is cut into windows of
+//   `win_rows` rows; owners are sorted by pair count and packed VB_SEG_OWNERS = 32 to a warp task.
+//   For task t and window w the task's pairs with a gather row inside w form nsteps[t][w]
+//   "super-steps" of 32 records (one per owner slot, 64 bytes); owners with fewer pairs in the
+//   window are padded with null records.  Record (16 bits):
+//       bits 15..5  gather row - w * win_rows        bits 4..0  count (0 = null)
+//   Pairs with count > 31 and all pairs of very short owners go to a residual CSR.
+//   The kernel binds LPO lanes to one owner slot (8 lanes x 2 FP64 columns, or 4 lanes x 4 fixed-point
+//   columns), so one warp step serves 32/LPO owners and the 32 slots of a super-step take LPO steps.
+// ----------------------------------------------------------------------------------------------
+#define VB_SEG_OWNERS 32
+#define VB_SEG_MAX_WARPS 22               // consumer warps per CTA (+1 producer warp)
+#define VB_SEG_CNT_BITS 5
+#define VB_SEG_MAX_COUNT 31
+#define VB_SEG_MAX_WIN_ROWS 2048
+#define VB_SEG_PREFETCH 3                 // super-steps of records in flight per warp
+
+struct SegSet {
+    int built;
+    int64_t n_owner, n_gather;
+    int64_t n_task;          // ceil(n_owner / 32) tasks in sorted order (longest owners first)
+    int64_t n_task_stream;   // the first n_task_stream tasks carry records; the rest only need the epilogue
+    int n_win, win_rows, nb; // windows of the table, rows per window, windows resident in shared memory
+    int64_t n_step;          // super-steps in total
+    int64_t n_light;         // pairs carried by the streams
+    int64_t n_heavy;         // pairs in the residual
+    int64_t max_reads;       // largest sum of counts over one owner's stream pairs (fixed-point error bound)
+    int32_t* perm;           // [n_task*32] owner id of each slot, -1 = padding
+    uint16_t* nsteps;        // [n_task_stream * n_win]
+    int64_t* task_off;       // [n_task_stream + 1] first super-step of each task
+    uint16_t* rec;           // [n_step*32 + slack]
+    int64_t* hptr;           // [n_owner+1] residual CSR
+    int32_t* hrow;
+    uint32_t* hcnt;
+    int grid, nwarps;
+    int64_t bytes;
+};
+
+struct SegView {
+    int64_t n_owner, n_gather, n_task, n_task_stream;
+    int n_win, win_rows;
+    const int32_t* __restrict__ perm;
+    const uint16_t* __restrict__ nsteps;
+    const int64_t* __restrict__ task_off;
+    const uint16_t* __restrict__ rec;
+    const int64_t* __restrict__ hptr;
+    const int32_t* __restrict__ hrow;
+    const uint32_t* __restrict__ hcnt;
+};
+
 struct vb_counts {
     int device;
     int sm_count;
@@ -93,11 +146,18 @@ struct vb_counts {
     GatherSet gA;           // cell pass
     GatherSet gB;           // SNP pass
     int gather_failed;      // a build attempt failed (message in vb_last_error); rows path is used
+    // window-segment formats (vb_seg.cu), index = table precision (0 FP64 rows of 128 B, 1 fixed-point rows of 64 B)
+    SegSet sA[2];           // cell pass
+    SegSet sB[2];           // SNP pass
+    int seg_failed[2];
 };
 
 // vb_gather.cu
 int vb_gather_build(vb_counts* m, cudaStream_t st);      // builds gA and gB once
 void vb_gather_free(vb_counts* m);
+// vb_seg.cu
+int vb_seg_build(vb_counts* m, int prec, cudaStream_t st);   // builds sA[prec] and sB[prec] once
+void vb_seg_free(vb_counts* m);
 
 // what the kernels see of the staged counts
 struct CountsView {
@@ -127,8 +187,11 @@ struct EmP {
     int* ctrl;
     // gather path (vb_gather.cu): Wt is then [B, 2V, 16] (rows of 128 bytes, columns replicated 16/KT times),
     // RP the same layout of ID_prob [B, C, 16], H the residual sums [B, max(C, 2V), 16]
-    int tiled, KT;
+    int tiled, KT;             // tiled: 0 row kernels, 1 gather-stream kernels, 2 window-segment kernels (FP64 tables),
+                               //        3 window-segment kernels (32-bit fixed-point tables)
     double *RP, *H;
+    uint32_t *Wq, *RPq;        // tiled == 3: fixed-point copies of Wt [B, 2V, 16] and RP [B, C, 16]
+    double* qscale;            // tiled == 3: [B] power of two with |W| * qscale < 2^32
     // block-partial layout inside part[b * part_stride + ...]
     int64_t part_stride;
     int off_theta, off_klgt, off_cell, off_klth;
@@ -227,6 +290,10 @@ int vb_gather_launch(const vb_counts* m, const EmP& p, int ori, int mode, int th
 int vb_pad_rows_launch(const vb_counts* m, const double* src, int64_t n_row, int K, int KT, int B, double* dst,
                        cudaStream_t st);
 enum { GM_CELL = 0, GM_CELL_LL = 1, GM_SNP = 2, GM_PLAIN = 3 };
+// vb_seg.cu
+void vb_seg_geometry(const SegSet& g, int* grid, int* nwarps);
+int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, cudaStream_t st);
+int vb_seg_quantise_rows(const vb_counts* m, const EmP& p, cudaStream_t st);   // RP -> RPq before the first SNP pass
 
 // error plumbing -------------------------------------------------------------------------------
 void vb_set_error(const char* fmt, ...);

@@ -388,6 +388,15 @@ __global__ void __launch_bounds__(2 * VB_MAX_GT * 32) k_theta(const EmP p, const
         double t = 0.0;
         for (int g = 0; g < G; ++g) t += kls[g];
         p.part[(size_t)b * p.part_stride + p.off_klth] = t;
+        if (p.tiled == 3) {
+            // fixed-point tables: every table entry is a convex combination of the A_g (or of the B_g), so
+            // |W| <= max_g max(|A_g|, |B_g|) < 2^e and -W * 2^(32-e) fits an unsigned 32-bit value
+            const double* ab = p.ab + (size_t)b * 2 * G;
+            double mx = 0.0;
+            for (int g = 0; g < 2 * G; ++g) mx = fmax(mx, fabs(ab[g]));
+            const int e = (mx > 0.0 && mx < 1e300) ? ilogb(mx) + 1 : 0;
+            p.qscale[b] = ldexp(1.0, 32 - e);
+        }
     }
 }
 
@@ -472,6 +481,14 @@ __global__ void __launch_bounds__(VB_THREADS) k_gt(const EmP p, const int do_gt)
             // gather-table rows of 128 bytes, columns replicated 16/KT times (vb_gather.cu)
             double* w0 = p.Wt + ((size_t)b * p.V + i) * 2 * VB_ROW_DOUBLES;
             for (int c = k; c < VB_ROW_DOUBLES; c += p.KT) { w0[c] = wb; w0[VB_ROW_DOUBLES + c] = wa; }
+            if (p.tiled == 3) {
+                const double qs = p.qscale[b];
+                const double fb = -wb * qs, fa = -wa * qs;
+                const uint32_t qb = fb >= 4294967295.0 ? 0xffffffffu : (fb > 0.0 ? (uint32_t)__double2ull_rn(fb) : 0u);
+                const uint32_t qa = fa >= 4294967295.0 ? 0xffffffffu : (fa > 0.0 ? (uint32_t)__double2ull_rn(fa) : 0u);
+                uint32_t* q0 = p.Wq + ((size_t)b * p.V + i) * 2 * VB_ROW_DOUBLES;
+                for (int c = k; c < VB_ROW_DOUBLES; c += p.KT) { q0[c] = qb; q0[VB_ROW_DOUBLES + c] = qa; }
+            }
         } else {
             Wt[(size_t)i * 2 * K + k] = wb;
             Wt[(size_t)i * 2 * K + K + k] = wa;
@@ -727,6 +744,7 @@ static bool tile_for(int K, int& KT, int& KR) {
     } while (0)
 
 static int launch_cell(const vb_counts* m, const EmP& p, int mode, cudaStream_t st) {
+    if (p.tiled >= 2) return vb_seg_launch(m, p, 0, mode == 0 ? GM_CELL : GM_CELL_LL, 0, st);
     if (p.tiled) return vb_gather_launch(m, p, 0, mode == 0 ? GM_CELL : GM_CELL_LL, 0, nullptr, st);
     int KT, KR;
     if (!tile_for(p.K, KT, KR)) { vb_set_error("n_donor=%d outside [1, %d]", p.K, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
@@ -738,6 +756,7 @@ static int launch_cell(const vb_counts* m, const EmP& p, int mode, cudaStream_t 
 }
 
 static int launch_snp(const vb_counts* m, const EmP& p, int theta_mode, cudaStream_t st) {
+    if (p.tiled >= 2) return vb_seg_launch(m, p, 1, GM_SNP, theta_mode, st);
     if (p.tiled) return vb_gather_launch(m, p, 1, GM_SNP, theta_mode, nullptr, st);
     int KT, KR;
     if (!tile_for(p.K, KT, KR)) { vb_set_error("n_donor=%d outside [1, %d]", p.K, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
@@ -751,16 +770,24 @@ static int launch_snp(const vb_counts* m, const EmP& p, int theta_mode, cudaStre
 // ---------------------------------------------------------------------------------------------
 // path selection: rows (v1, one warp per row, L2 gathers) or gather (vb_gather.cu, ring-slab streams)
 // ---------------------------------------------------------------------------------------------
-static int g_path = 0;                       // 0 auto, 1 rows, 2 gather
+static int g_path = 0;                       // 0 auto, 1 rows, 2 gather, 3 segments (FP64 tables), 4 segments (fixed-point tables)
 #define VB_GATHER_MIN_NNZ (4ll << 20)        // below this the passes are launch/latency bound either way
 
-extern "C" void vb_set_path(int mode) { g_path = mode < 0 || mode > 2 ? 0 : mode; }
+extern "C" void vb_set_path(int mode) { g_path = mode < 0 || mode > 4 ? 0 : mode; }
 
-// *use = 1 when the gather kernels serve this (counts, K); builds the formats on first use
-static int want_gather(const vb_counts* mc, int K, int* use) {
+// *use = kernel family serving this (counts, K): 0 rows, 1 gather streams, 2 window segments with FP64 tables,
+// 3 window segments with fixed-point tables (`fixed_ok`: the caller can build them); builds the formats on first use
+static int want_gather(const vb_counts* mc, int K, int fixed_ok, int* use) {
     vb_counts* m = const_cast<vb_counts*>(mc);
     *use = 0;
     if (g_path == 1 || K > VB_ROW_DOUBLES) return VB_OK;
+    if (g_path == 3 || g_path == 4) {
+        const int prec = (g_path == 4 && fixed_ok) ? 1 : 0;
+        const int rc = vb_seg_build(m, prec, 0);
+        if (rc) return rc;
+        *use = 2 + prec;
+        return VB_OK;
+    }
     if (g_path == 0 && (m->N < VB_GATHER_MIN_NNZ || m->gather_failed)) return VB_OK;
     const int rc = vb_gather_build(m, 0);
     if (rc) return g_path == 2 ? rc : VB_OK;
@@ -777,13 +804,23 @@ static int kt_for(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : 16); }
 
 static void part_layout(const vb_counts* m, EmP& p) {
     int ga = 0, gb = 0, nw;
-    if (m->gA.built) { vb_gather_geometry(m, m->gA, &ga, &nw); vb_gather_geometry(m, m->gB, &gb, &nw); }
-    p.n_snpblk = p.tiled ? gb : m->grid_snp;
+    int cap_snp = m->grid_snp, cap_cell = m->grid_cell;
+    if (m->gA.built) {
+        vb_gather_geometry(m, m->gA, &ga, &nw); vb_gather_geometry(m, m->gB, &gb, &nw);
+        if (ga > cap_cell) cap_cell = ga;
+        if (gb > cap_snp) cap_snp = gb;
+    }
+    int sa[2] = {0, 0}, sb[2] = {0, 0};
+    for (int q = 0; q < 2; ++q)
+        if (m->sA[q].built && m->sB[q].built) {
+            vb_seg_geometry(m->sA[q], &sa[q], &nw); vb_seg_geometry(m->sB[q], &sb[q], &nw);
+            if (sa[q] > cap_cell) cap_cell = sa[q];
+            if (sb[q] > cap_snp) cap_snp = sb[q];
+        }
+    p.n_snpblk = p.tiled >= 2 ? sb[p.tiled - 2] : (p.tiled ? gb : m->grid_snp);
     p.n_elemblk = m->grid_elem;
-    p.n_cellblk = p.tiled ? ga : m->grid_cell;
+    p.n_cellblk = p.tiled >= 2 ? sa[p.tiled - 2] : (p.tiled ? ga : m->grid_cell);
     p.n_klth = (p.bmm || p.ase) ? m->grid_elem : 1;
-    const int cap_snp = gb > m->grid_snp ? gb : m->grid_snp;
-    const int cap_cell = ga > m->grid_cell ? ga : m->grid_cell;
     p.off_theta = 0;
     p.off_klgt = p.off_theta + cap_snp * 2 * VB_MAX_GT;
     p.off_cell = p.off_klgt + p.n_elemblk;
@@ -814,10 +851,15 @@ static int fill_vireo(const vb_counts* m, const vb_vireo_args* a, EmP& p) {
     }
     {
         int use = 0;
-        const int rc = want_gather(m, p.K, &use);
+        const int rc = want_gather(m, p.K, !p.ase, &use);
         if (rc) return rc;
         p.tiled = use; p.KT = kt_for(p.K); p.RP = a->rpad; p.H = a->heavy;
         if (use && (!p.RP || !p.H)) { vb_set_error("rpad / heavy workspace is NULL (see vb_vireo_ws_sizes)"); return VB_E_ARG; }
+        if (use == 3) {   // fixed-point copies live behind the FP64 tables of the same workspaces
+            p.Wq = reinterpret_cast<uint32_t*>(p.Wt + (size_t)p.B * p.V * 2 * VB_ROW_DOUBLES);
+            p.RPq = reinterpret_cast<uint32_t*>(p.RP + (size_t)p.B * p.C * VB_ROW_DOUBLES);
+            p.qscale = p.ab + (size_t)p.B * p.T * 2 * p.G;
+        }
     }
     if ((p.id_rows != 1 && p.id_rows != m->C) || (p.thp_rows != 1 && p.thp_rows != p.T)) {
         vb_set_error("prior rows must be 1 or the full extent");
@@ -848,7 +890,7 @@ static int fill_bmm(const vb_counts* m, const vb_bmm_args* a, EmP& p) {
     }
     {
         int use = 0;
-        const int rc = want_gather(m, p.K, &use);
+        const int rc = want_gather(m, p.K, 0, &use);
         if (rc) return rc;
         p.tiled = use; p.KT = kt_for(p.K); p.RP = a->rpad; p.H = a->heavy;
         if (use && (!p.RP || !p.H)) { vb_set_error("rpad / heavy workspace is NULL (see vb_bmm_ws_sizes)"); return VB_E_ARG; }
@@ -864,7 +906,7 @@ static int ws_sizes(const vb_counts* m, int K, int G, int B, int T_is_V, vb_ws_s
     memset(&p, 0, sizeof(p));
     p.bmm = G == 0; p.ase = T_is_V;
     int use = 0;
-    const int rc = want_gather(m, K, &use);
+    const int rc = want_gather(m, K, G != 0 && !T_is_V, &use);
     if (rc) return rc;
     p.tiled = use;
     part_layout(m, p);
@@ -873,9 +915,13 @@ static int ws_sizes(const vb_counts* m, int K, int G, int B, int T_is_V, vb_ws_s
     out->S = (int64_t)B * m->V * K;
     out->W = (int64_t)B * m->V * Kw * 2;
     out->rpad = use ? (int64_t)B * m->C * VB_ROW_DOUBLES : 0;
+    if (use == 3) {   // fixed-point copies (4 bytes per entry) behind the FP64 tables
+        out->W += (int64_t)B * m->V * VB_ROW_DOUBLES;
+        out->rpad += (int64_t)B * m->C * (VB_ROW_DOUBLES / 2);
+    }
     out->heavy = use ? (int64_t)B * (m->C > 2 * m->V ? m->C : 2 * m->V) * VB_ROW_DOUBLES : 0;
     out->loglik = (int64_t)B * m->C * K;
-    out->ab = (int64_t)B * T * 2 * (G ? G : 1);
+    out->ab = (int64_t)B * T * 2 * (G ? G : 1) + (use == 3 ? B : 0);
     out->part = (int64_t)B * p.part_stride;
     out->scal = (int64_t)B * VB_SCAL_N;
     out->ctrl = (int64_t)B * VB_CTRL_N;
@@ -941,7 +987,8 @@ static int run_loop(const vb_counts* m, const EmP& p, int poll_every, cudaStream
     }
     VB_CUDA(cudaMemsetAsync(p.ctrl, 0, n_ctrl * sizeof(int32_t), st));
     if (p.tiled) {   // the SNP pass gathers ID_prob from its 128-byte-row copy
-        const int rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.B, p.RP, st);
+        int rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.B, p.RP, st);
+        if (!rc && p.tiled == 3) rc = vb_seg_quantise_rows(m, p, st);
         if (rc) return rc;
     }
     if (poll_every <= 0) poll_every = 16;
@@ -987,6 +1034,7 @@ extern "C" int vb_vireo_step(const vb_counts* m, const vb_vireo_args* a, int pha
     p.ctrl = nullptr;                       // single phases never consult the loop state
     if (p.tiled && (phases & VB_PH_SNP)) {
         rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.B, p.RP, (cudaStream_t)stream);
+        if (!rc && p.tiled == 3) rc = vb_seg_quantise_rows(m, p, (cudaStream_t)stream);
         if (rc) return rc;
     }
     return vireo_iteration(m, p, phases, false, (cudaStream_t)stream);

@@ -1,0 +1,784 @@
+// vb_seg.cu -- the window-segment kernels: both sparse passes of the EM iteration with the gathered
+// table staged window by window through shared memory (cp.async.bulk + mbarrier) and a small lane
+// group bound to every owner row.
+//
+// Both passes are "for every owner: sum over its pairs of count * table[gather row][0:16]":
+//   cell pass  logLik_ID[j,:] = sum_i  (dp-ad)_ij * W[2i,:] + ad_ij * W[2i+1,:]
+//              (vireoSNP/utils/vireo_model.py:190-196, bmm_model.py:125-129)
+//   SNP  pass  S2[i,:] = sum_j (dp-ad)_ij * ID_prob[j,:],  S1[i,:] = sum_j ad_ij * ID_prob[j,:]
+//              (vireo_model.py:168-170,207-209, bmm_model.py:136-138)
+// What bounds such a pass on B200 is the shared-memory crossbar (128 B/clk/SM): every pair needs one
+// table row.  The lane-per-owner kernels of vb_gather.cu spend 1.5 crossbar wavefronts per 128-byte
+// row because a quarter warp is rarely full.  Here
+//   * LPO lanes share one owner: the 8 (FP64) or 4 (fixed point) lanes read one contiguous row with a
+//     single 16-byte load each, so a wavefront always carries whole rows and is never bank-conflicted;
+//   * a warp task holds 32 owners: 32/LPO of them are served per warp step, the accumulators of all
+//     32 stay in registers (static indexing: the slot index is the unrolled loop variable);
+//   * the table streams through NB window buffers; a producer warp refills a buffer when every
+//     consumer warp has released it (full/empty mbarriers), consumers wait per window, not per record;
+//   * the records of a task are stored per window as super-steps of 32 x 16 bits, prefetched from
+//     global memory VB_SEG_PREFETCH super-steps ahead;
+//   * PREC 1 keeps the table as unsigned 32-bit fixed point (rows of 64 bytes: half the crossbar and
+//     L2 traffic) and accumulates count * value exactly in 64-bit integers, so the result does not
+//     depend on the summation order; the quantisation error is bounded per owner by
+//     sum(count) * 2^-33 * range and reported by vb_counts_info.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <stdlib.h>
+#include <string.h>
+
+#include <type_traits>
+#include <vector>
+
+#include "vb_common.cuh"
+#include "vb_stream.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// build kernels
+// ---------------------------------------------------------------------------------------------
+
+// pairs per owner: stream pairs (count <= 31), residual pairs, reads carried by the stream pairs
+template <int ORI, bool WIDE>
+__global__ void k_sg_count(const CountsView m, int64_t n_owner, uint32_t* __restrict__ n_light, uint32_t* __restrict__ n_heavy,
+                           uint32_t* __restrict__ reads, unsigned int* flags) {
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n_owner; o += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t nl = 0, nh = 0, rd = 0;
+        const bool ok = for_records<ORI, WIDE>(m, o, [&](int, uint32_t c) {
+            if (c > VB_SEG_MAX_COUNT) ++nh;
+            else { ++nl; rd += c; }
+        });
+        if (!ok) atomicOr(&flags[0], 1u);
+        n_light[o] = nl;
+        n_heavy[o] = nh;
+        reads[o] = rd;
+    }
+}
+
+__global__ void k_sg_iota(int32_t* out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int32_t)i;
+}
+
+// owners at sorted ranks >= first_sparse are served by the residual kernel entirely
+__global__ void k_sg_mark_sparse(const int32_t* __restrict__ perm_sorted, int64_t first_sparse, int64_t n_owner,
+                                 uint8_t* __restrict__ sparse, uint32_t* __restrict__ n_light, uint32_t* __restrict__ n_heavy,
+                                 uint32_t* __restrict__ reads) {
+    for (int64_t r = first_sparse + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_owner; r += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t o = perm_sorted[r];
+        sparse[o] = 1;
+        n_heavy[o] += n_light[o];
+        n_light[o] = 0;
+        reads[o] = 0;
+    }
+}
+
+__global__ void k_sg_sums(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, const uint32_t* __restrict__ c,
+                          int64_t n, unsigned long long* out) {
+    unsigned long long sa = 0, sb = 0, mc = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        sa += a[i]; sb += b[i];
+        mc = c[i] > mc ? c[i] : mc;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        sa += __shfl_xor_sync(VB_FULL, sa, off);
+        sb += __shfl_xor_sync(VB_FULL, sb, off);
+        const unsigned long long o = __shfl_xor_sync(VB_FULL, mc, off);
+        mc = o > mc ? o : mc;
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, sa); atomicAdd(out + 1, sb); atomicMax(out + 2, mc); }
+}
+
+// pairs of each stream owner per table window; one thread per sorted position
+template <int ORI, bool WIDE>
+__global__ void k_sg_wincount(const CountsView m, int64_t n_active, const int32_t* __restrict__ perm, int win_rows, int n_win,
+                              uint16_t* __restrict__ cnt) {
+    for (int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pos < n_active; pos += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = perm[pos];
+        uint16_t* row = cnt + (size_t)pos * n_win;
+        int w = 0;
+        uint32_t n = 0;
+        for_records<ORI, WIDE>(m, o, [&](int g, uint32_t c) {
+            if (c > VB_SEG_MAX_COUNT) return;
+            const int gw = g / win_rows;
+            if (gw != w) { if (n) row[w] = (uint16_t)n; w = gw; n = 0; }
+            ++n;
+        });
+        if (n) row[w] = (uint16_t)n;
+    }
+}
+
+// super-steps of (task, window) = the largest pair count among the task's 32 owners
+__global__ void k_sg_taskmax(const uint16_t* __restrict__ cnt, int64_t n_active, int64_t n_task_stream, int n_win,
+                             uint16_t* __restrict__ nsteps, int64_t* __restrict__ wide) {
+    const int64_t n = n_task_stream * n_win;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e <= n; e += (int64_t)gridDim.x * blockDim.x) {
+        if (e == n) { wide[e] = 0; continue; }
+        const int64_t t = e / n_win;
+        const int w = (int)(e - t * n_win);
+        uint16_t mx = 0;
+        for (int s = 0; s < VB_SEG_OWNERS; ++s) {
+            const int64_t pos = t * VB_SEG_OWNERS + s;
+            if (pos < n_active) { const uint16_t c = cnt[(size_t)pos * n_win + w]; mx = c > mx ? c : mx; }
+        }
+        nsteps[e] = mx;
+        wide[e] = mx;
+    }
+}
+
+__global__ void k_sg_widen(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = i < n ? (int64_t)in[i] : 0;
+}
+
+// write the records and the residual CSR; one thread per sorted position
+template <int ORI, bool WIDE>
+__global__ void k_sg_fill(const CountsView m, int64_t n_owner, int64_t n_active, const int32_t* __restrict__ perm, int win_rows,
+                          int n_win, const int64_t* __restrict__ step_off, uint16_t* __restrict__ rec,
+                          const int64_t* __restrict__ hptr, int32_t* __restrict__ hrow, uint32_t* __restrict__ hcnt) {
+    for (int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pos < n_owner; pos += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = perm[pos];
+        const bool streams = pos < n_active;
+        const int64_t t = pos / VB_SEG_OWNERS;
+        const int slot = (int)(pos % VB_SEG_OWNERS);
+        int64_t h = hptr[o];
+        int w = -1;
+        int64_t s = 0;
+        for_records<ORI, WIDE>(m, o, [&](int g, uint32_t c) {
+            if (c > VB_SEG_MAX_COUNT || !streams) { hrow[h] = g; hcnt[h] = c; ++h; return; }
+            const int gw = g / win_rows;
+            if (gw != w) { w = gw; s = step_off[t * n_win + w]; }
+            rec[(size_t)s * VB_SEG_OWNERS + slot] = (uint16_t)(((uint32_t)(g - gw * win_rows) << VB_SEG_CNT_BITS) | c);
+            ++s;
+        });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: build one orientation
+// ---------------------------------------------------------------------------------------------
+static void seg_set_free(SegSet& g) {
+    cudaFree(g.perm); cudaFree(g.nsteps); cudaFree(g.task_off); cudaFree(g.rec);
+    cudaFree(g.hptr); cudaFree(g.hrow); cudaFree(g.hcnt);
+    memset(&g, 0, sizeof(g));
+}
+
+static CountsView sg_view(const vb_counts* m) {
+    CountsView v;
+    v.C = m->C; v.V = m->V; v.N = m->N;
+    v.cell_ptr = m->cell_ptr; v.cell_idx = m->cell_idx; v.cell_cnt = m->cell_cnt; v.cell_dp = m->cell_dp;
+    v.snp_ptr = m->snp_ptr; v.snp_idx = m->snp_idx; v.snp_cnt = m->snp_cnt; v.snp_dp = m->snp_dp;
+    return v;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// window geometry per table precision: rows per window and resident windows (shared memory: nb * rows * row bytes)
+static void seg_window(int prec, int* win_rows, int* nb) {
+    if (prec == 0) { *win_rows = env_int("VIREO_B200_SEG_WR64", 768); *nb = env_int("VIREO_B200_SEG_NB64", 2); }
+    else { *win_rows = env_int("VIREO_B200_SEG_WR32", 1024); *nb = env_int("VIREO_B200_SEG_NB32", 3); }
+    if (*win_rows < 32) *win_rows = 32;
+    if (*win_rows > VB_SEG_MAX_WIN_ROWS) *win_rows = VB_SEG_MAX_WIN_ROWS;
+    *win_rows &= ~7;
+    if (*nb < 2) *nb = 2;
+    const int row_bytes = prec == 0 ? 128 : 64;
+    while ((size_t)*nb * *win_rows * row_bytes > 200 * 1024 && *nb > 2) --*nb;
+    while ((size_t)*nb * *win_rows * row_bytes > 200 * 1024) *win_rows -= 8;
+}
+
+template <int ORI>
+static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
+    memset(&g, 0, sizeof(g));
+    const int sm = m->sm_count;
+    const int64_t O = ORI == 0 ? m->C : 2 * m->V;
+    const int64_t Gn = ORI == 0 ? 2 * m->V : m->C;
+    if (O >= (1ll << 31) - 64 || Gn >= (1ll << 31) - 4096) { vb_set_error("segment format: more than 2^31 rows"); return VB_E_UNSUPPORTED; }
+    int win_rows, nb;
+    seg_window(prec, &win_rows, &nb);
+    int n_win = (int)((Gn + win_rows - 1) / win_rows);
+    if (n_win < 1) n_win = 1;
+    const int64_t n_task = (O + VB_SEG_OWNERS - 1) / VB_SEG_OWNERS;
+    const CountsView v = sg_view(m);
+    GsScratch tmp;
+    int rc;
+    uint32_t *nl, *nh, *rd, *nl_sorted;
+    int32_t *ids, *perm_sorted;
+    unsigned int* flags;
+    unsigned long long* sums;
+    uint8_t* sparse;
+    if ((rc = tmp.alloc(&nl, O)) || (rc = tmp.alloc(&nh, O + 1)) || (rc = tmp.alloc(&rd, O)) || (rc = tmp.alloc(&nl_sorted, O)) ||
+        (rc = tmp.alloc(&ids, O)) || (rc = tmp.alloc(&perm_sorted, O)) || (rc = tmp.alloc(&flags, 4)) ||
+        (rc = tmp.alloc(&sums, 4)) || (rc = tmp.alloc(&sparse, O)))
+        return rc;
+    VB_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(unsigned int), st));
+    VB_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(unsigned long long), st));
+    VB_CUDA(cudaMemsetAsync(sparse, 0, O ? O : 1, st));
+    unsigned int hflags[4] = {0, 0, 0, 0};
+    unsigned long long hsums[4] = {0, 0, 0, 0};
+    std::vector<uint32_t> hlen((size_t)O, 0u);
+    int64_t n_active = 0;
+    if (O) {
+        if (m->wide) k_sg_count<ORI, true><<<grid1d(O, sm), 256, 0, st>>>(v, O, nl, nh, rd, flags);
+        else k_sg_count<ORI, false><<<grid1d(O, sm), 256, 0, st>>>(v, O, nl, nh, rd, flags);
+        VB_CUDA(cudaGetLastError());
+        k_sg_iota<<<grid1d(O, sm), 256, 0, st>>>(ids, O);
+        VB_CUDA(cudaGetLastError());
+        size_t tb = 0;
+        VB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, nl, nl_sorted, ids, perm_sorted, O, 0, 32, st));
+        void* cub_tmp;
+        if ((rc = tmp.alloc((unsigned char**)&cub_tmp, tb))) return rc;
+        VB_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_tmp, tb, nl, nl_sorted, ids, perm_sorted, O, 0, 32, st));
+        VB_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaMemcpyAsync(hlen.data(), nl_sorted, O * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        if (hflags[0]) { vb_set_error("segment format: an entry has AD > DP"); return VB_E_VALUE; }
+        // Owners with very few pairs would pad a whole task's super-steps for one or two records; when such owners
+        // carry a negligible share of the pairs (e.g. alternative-allele rows of homozygous-reference SNPs) they
+        // are served by the residual kernel instead.
+        double total = 0.0;
+        for (int64_t r = 0; r < O; ++r) total += hlen[r];
+        int64_t first_sparse = O, moved = 0;
+        const int64_t budget = (int64_t)(total / 50.0);
+        while (first_sparse > 0 && hlen[first_sparse - 1] <= VB_SPARSE_LEN && moved + hlen[first_sparse - 1] <= budget) {
+            moved += hlen[first_sparse - 1];
+            --first_sparse;
+        }
+        if (moved > 0) {
+            k_sg_mark_sparse<<<grid1d(O - first_sparse, sm), 256, 0, st>>>(perm_sorted, first_sparse, O, sparse, nl, nh, rd);
+            VB_CUDA(cudaGetLastError());
+            for (int64_t r = first_sparse; r < O; ++r) hlen[r] = 0;
+        }
+        n_active = first_sparse;
+        while (n_active > 0 && hlen[n_active - 1] == 0) --n_active;
+        k_sg_sums<<<grid1d(O, sm), 256, 0, st>>>(nl, nh, rd, O, sums);
+        VB_CUDA(cudaGetLastError());
+        VB_CUDA(cudaMemcpyAsync(hsums, sums, sizeof(hsums), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+    }
+    g.n_owner = O; g.n_gather = Gn; g.n_task = n_task; g.n_win = n_win; g.win_rows = win_rows; g.nb = nb;
+    g.n_light = (int64_t)hsums[0]; g.n_heavy = (int64_t)hsums[1]; g.max_reads = (int64_t)hsums[2];
+    g.n_task_stream = (n_active + VB_SEG_OWNERS - 1) / VB_SEG_OWNERS;
+    const int64_t nts = g.n_task_stream;
+
+    VB_CUDA(cudaMalloc(&g.perm, (n_task ? n_task : 1) * VB_SEG_OWNERS * sizeof(int32_t)));
+    VB_CUDA(cudaMemsetAsync(g.perm, 0xff, (n_task ? n_task : 1) * VB_SEG_OWNERS * sizeof(int32_t), st));
+    if (O) VB_CUDA(cudaMemcpyAsync(g.perm, perm_sorted, O * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+
+    // super-steps per (task, window) and their offsets
+    const int64_t n_tw = nts * n_win;
+    uint16_t* cnt_ow;
+    int64_t *wide, *step_off;
+    if ((rc = tmp.alloc(&cnt_ow, (size_t)(n_active ? n_active : 1) * n_win)) || (rc = tmp.alloc(&wide, n_tw + 1)) ||
+        (rc = tmp.alloc(&step_off, n_tw + 1)))
+        return rc;
+    VB_CUDA(cudaMalloc(&g.nsteps, (n_tw ? n_tw : 1) * sizeof(uint16_t)));
+    VB_CUDA(cudaMalloc(&g.task_off, (nts + 1) * sizeof(int64_t)));
+    VB_CUDA(cudaMemsetAsync(cnt_ow, 0, (size_t)(n_active ? n_active : 1) * n_win * sizeof(uint16_t), st));
+    if (n_active) {
+        if (m->wide) k_sg_wincount<ORI, true><<<grid1d(n_active, sm), 256, 0, st>>>(v, n_active, g.perm, win_rows, n_win, cnt_ow);
+        else k_sg_wincount<ORI, false><<<grid1d(n_active, sm), 256, 0, st>>>(v, n_active, g.perm, win_rows, n_win, cnt_ow);
+        VB_CUDA(cudaGetLastError());
+    }
+    k_sg_taskmax<<<grid1d(n_tw + 1, sm), 256, 0, st>>>(cnt_ow, n_active, nts, n_win, g.nsteps, wide);
+    VB_CUDA(cudaGetLastError());
+    {
+        size_t tb = 0;
+        VB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, wide, step_off, n_tw + 1, st));
+        void* cub_tmp;
+        if ((rc = tmp.alloc((unsigned char**)&cub_tmp, tb))) return rc;
+        VB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, wide, step_off, n_tw + 1, st));
+    }
+    int64_t total_steps = 0;
+    VB_CUDA(cudaMemcpyAsync(&total_steps, step_off + n_tw, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VB_CUDA(cudaMemcpy2DAsync(g.task_off, sizeof(int64_t), step_off, (size_t)n_win * sizeof(int64_t), sizeof(int64_t),
+                              (size_t)(nts + 1), cudaMemcpyDeviceToDevice, st));
+    VB_CUDA(cudaStreamSynchronize(st));
+    g.n_step = total_steps;
+
+    // residual CSR
+    VB_CUDA(cudaMalloc(&g.hptr, (O + 1) * sizeof(int64_t)));
+    VB_CUDA(cudaMalloc(&g.hrow, (g.n_heavy ? g.n_heavy : 1) * sizeof(int32_t)));
+    VB_CUDA(cudaMalloc(&g.hcnt, (g.n_heavy ? g.n_heavy : 1) * sizeof(uint32_t)));
+    {
+        int64_t* hw;
+        if ((rc = tmp.alloc(&hw, O + 1))) return rc;
+        k_sg_widen<<<grid1d(O + 1, sm), 256, 0, st>>>(nh, O, hw);
+        VB_CUDA(cudaGetLastError());
+        size_t tb = 0;
+        VB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, hw, g.hptr, O + 1, st));
+        void* cub_tmp;
+        if ((rc = tmp.alloc((unsigned char**)&cub_tmp, tb))) return rc;
+        VB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, hw, g.hptr, O + 1, st));
+    }
+    const size_t n_rec = ((size_t)total_steps + VB_SEG_PREFETCH + 1) * VB_SEG_OWNERS;   // slack: the prefetch runs ahead
+    VB_CUDA(cudaMalloc(&g.rec, n_rec * sizeof(uint16_t)));
+    VB_CUDA(cudaMemsetAsync(g.rec, 0, n_rec * sizeof(uint16_t), st));
+    if (O) {
+        if (m->wide) k_sg_fill<ORI, true><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, win_rows, n_win, step_off, g.rec, g.hptr, g.hrow, g.hcnt);
+        else k_sg_fill<ORI, false><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, win_rows, n_win, step_off, g.rec, g.hptr, g.hrow, g.hcnt);
+        VB_CUDA(cudaGetLastError());
+    }
+    VB_CUDA(cudaStreamSynchronize(st));
+
+    // launch geometry: one CTA per SM, as few consumer warps as cover the streaming tasks
+    int nw = (int)((nts + sm - 1) / sm);
+    if (nw < 1) nw = 1;
+    if (nw > VB_SEG_MAX_WARPS) nw = VB_SEG_MAX_WARPS;
+    int64_t grid = (nts + nw - 1) / nw;
+    if (grid < 1) grid = 1;
+    if (grid > 65535 * 16) { vb_set_error("segment format: too many owner rows"); return VB_E_UNSUPPORTED; }
+    g.grid = (int)grid; g.nwarps = nw;
+    g.bytes = (int64_t)n_rec * 2 + n_task * VB_SEG_OWNERS * 4 + n_tw * 2 + (nts + 1) * 8 + (O + 1) * 8 + g.n_heavy * 8;
+    g.built = 1;
+    return VB_OK;
+}
+
+int vb_seg_build(vb_counts* m, int prec, cudaStream_t st) {
+    if (prec < 0 || prec > 1) { vb_set_error("bad table precision"); return VB_E_ARG; }
+    if (m->sA[prec].built && m->sB[prec].built) return VB_OK;
+    if (m->seg_failed[prec]) return VB_E_UNSUPPORTED;
+    int rc = seg_build_one<0>(m, m->sA[prec], prec, st);
+    if (!rc) rc = seg_build_one<1>(m, m->sB[prec], prec, st);
+    if (rc) {
+        seg_set_free(m->sA[prec]);
+        seg_set_free(m->sB[prec]);
+        m->seg_failed[prec] = 1;
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+void vb_seg_free(vb_counts* m) {
+    for (int i = 0; i < 2; ++i) { seg_set_free(m->sA[i]); seg_set_free(m->sB[i]); }
+}
+
+void vb_seg_geometry(const SegSet& g, int* grid, int* nwarps) {
+    *grid = g.grid > 0 ? g.grid : 1;
+    *nwarps = g.nwarps > 0 ? g.nwarps : 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// residual pairs: one warp per owner, table rows gathered from L2 (always the FP64 table).
+// out[o][0:16] is written for EVERY owner (zeros where there is no residual).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VB_THREADS)
+k_seg_heavy(int64_t n_owner, const int64_t* __restrict__ hptr, const int32_t* __restrict__ hrow, const uint32_t* __restrict__ hcnt,
+            const double* __restrict__ table, int64_t table_stride, double* __restrict__ out, int64_t out_stride,
+            const int* __restrict__ ctrl) {
+    const int b = blockIdx.y;
+    if (ctrl && ctrl[b * VB_CTRL_N]) return;
+    const double* __restrict__ T = table + (size_t)b * table_stride;
+    double* __restrict__ O = out + (size_t)b * out_stride;
+    const int lane = threadIdx.x & 31, kl = lane & 15, sub = lane >> 4;
+    const int64_t nw = (int64_t)gridDim.x * VB_WARPS;
+    for (int64_t o = (int64_t)blockIdx.x * VB_WARPS + (threadIdx.x >> 5); o < n_owner; o += nw) {
+        const int64_t p0 = hptr[o], p1 = hptr[o + 1];
+        double acc = 0.0;
+        for (int64_t q = p0 + sub; q < p1; q += 2)
+            acc = fma((double)hcnt[q], T[(size_t)hrow[q] * VB_ROW_DOUBLES + kl], acc);
+        acc += __shfl_xor_sync(VB_FULL, acc, 16);
+        if (sub == 0) O[(size_t)o * VB_ROW_DOUBLES + kl] = acc;
+    }
+}
+
+// ID_prob rows [B*C, 16] -> unsigned 32-bit fixed point (value * 2^32, saturated)
+__device__ __forceinline__ uint32_t quant_unit(double r) {
+    const double s = r * 4294967296.0;
+    return s >= 4294967295.0 ? 0xffffffffu : (s > 0.0 ? (uint32_t)__double2ull_rn(s) : 0u);
+}
+
+__global__ void __launch_bounds__(VB_THREADS) k_seg_quant_rows(const double* __restrict__ src, int64_t n, uint32_t* __restrict__ dst) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        dst[e] = quant_unit(src[e]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_seg
+// ---------------------------------------------------------------------------------------------
+#define VB_SG_RED_DOUBLES (2 * VB_MAX_GT)
+#define VB_SG_PIECE 16384u          // bytes per bulk copy
+
+struct SegArgs {
+    int mode;            // GM_CELL, GM_CELL_LL, GM_SNP
+    int theta_mode;      // GM_SNP: 0 never, 1 always, 2 per the device iteration counter
+    int nwarps;          // consumer warps per CTA (block size = (nwarps + 1) * 32)
+    int nb;              // resident windows
+    int has_heavy;       // add p.H[owner] before the epilogue
+    int64_t table_stride;    // bytes per restart of the gather table
+    const unsigned char* table;
+};
+
+template <int PREC> struct SegCfg;
+template <> struct SegCfg<0> { static constexpr int LPO = 8, NC = 2, ROWB = 128, ROW_SHIFT = 2; };
+template <> struct SegCfg<1> { static constexpr int LPO = 4, NC = 4, ROWB = 64, ROW_SHIFT = 1; };
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// one owner slot of one super-step: PREC 0
+__device__ __forceinline__ void seg_step(uint32_t r, uint32_t base, double (&a)[2]) {
+    const uint32_t c = r & VB_SEG_MAX_COUNT;
+    if (c) {
+        double vx, vy;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(base + ((r & 0xffe0u) << 2)));
+        const double d = (double)(int)c;
+        a[0] = fma(d, vx, a[0]);
+        a[1] = fma(d, vy, a[1]);
+    }
+}
+// PREC 1: exact integer accumulation of count * fixed-point value
+__device__ __forceinline__ void seg_step(uint32_t r, uint32_t base, unsigned long long (&a)[4]) {
+    const uint32_t c = r & VB_SEG_MAX_COUNT;
+    if (c) {
+        uint32_t v0, v1, v2, v3;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(base + ((r & 0xffe0u) << 1)));
+        a[0] += (unsigned long long)c * v0;
+        a[1] += (unsigned long long)c * v1;
+        a[2] += (unsigned long long)c * v2;
+        a[3] += (unsigned long long)c * v3;
+    }
+}
+
+template <int PREC>
+__global__ void __launch_bounds__((VB_SEG_MAX_WARPS + 1) * 32, 1)
+k_seg(const SegView sv, const EmP p, const SegArgs sa) {
+    using Cfg = SegCfg<PREC>;
+    constexpr int LPO = Cfg::LPO, M = Cfg::LPO, NC = Cfg::NC, ROWB = Cfg::ROWB;
+    typedef typename std::conditional<PREC == 0, double, unsigned long long>::type acc_t;
+    typedef typename std::conditional<PREC == 0, uint4, uint2>::type chunk_t;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int b = blockIdx.y;
+    if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
+    const bool do_theta = sa.mode == GM_SNP && !p.bmm && vb_theta_on(p, b, sa.theta_mode);
+    if (sa.mode == GM_SNP && !p.bmm && !do_theta && !p.learn_gt && sa.theta_mode == 2) return;   // S1/S2 unused this iteration
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int NW = sa.nwarps, NB = sa.nb;
+    const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
+    const uint32_t win_bytes = (uint32_t)sv.win_rows * ROWB;
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t bars = ring + (uint32_t)NB * win_bytes;        // full[NB] then empty[NB]
+    double* red = reinterpret_cast<double*>(smem + (size_t)NB * win_bytes + 16 * 8);
+
+    // tasks are dealt to CTAs in boustrophedon order of the sorted list: warp ww of CTA c serves task
+    // ww * grid + (ww odd ? grid - 1 - c : c), so every CTA gets the same mix of long and short tasks
+    int64_t task = -1;
+    int nstream = 0;
+    for (int ww = 0; ww < NW; ++ww) {
+        const int64_t t = (int64_t)ww * grid + ((ww & 1) ? grid - 1 - cta : cta);
+        if (t < sv.n_task_stream) { ++nstream; if (ww == w) task = t; }
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NB; ++i) { mbar_init(bars + 8 * i, 1); mbar_init(bars + 8 * (NB + i), nstream > 0 ? nstream : 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    acc_t acc[M][NC];
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[i][c] = 0;
+
+    const int g = lane / LPO, sub = lane % LPO;
+    if (w == NW) {
+        // ---------------- producer warp: stream the table through the window buffers
+        if (nstream > 0) {
+            const unsigned char* __restrict__ T = sa.table + (size_t)b * sa.table_stride;
+            int bi = 0;
+            uint32_t use = 0;                               // how often buffer bi has been filled before
+            for (int wd = 0; wd < sv.n_win; ++wd) {
+                if (use > 0) mbar_wait(bars + 8 * (NB + bi), (use - 1) & 1);      // every consumer released the previous fill
+                if (lane == 0) {
+                    const int64_t r0 = (int64_t)wd * sv.win_rows;
+                    const int64_t rows = sv.n_gather - r0 < sv.win_rows ? sv.n_gather - r0 : sv.win_rows;
+                    const uint32_t bytes = (uint32_t)(rows * ROWB);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(bars + 8 * bi, bytes);
+                    const unsigned char* src = T + (size_t)r0 * ROWB;
+                    const uint32_t dst = ring + (uint32_t)bi * win_bytes;
+                    for (uint32_t off = 0; off < bytes; off += VB_SG_PIECE) {
+                        const uint32_t sz = bytes - off < VB_SG_PIECE ? bytes - off : VB_SG_PIECE;
+                        bulk_g2s(dst + off, src + off, sz, bars + 8 * bi);
+                    }
+                }
+                __syncwarp();
+                if (++bi == NB) { bi = 0; ++use; }
+            }
+        }
+    } else if (task >= 0) {
+        // ---------------- consumer warp: 32 owner slots, LPO lanes per slot
+        const unsigned char* sp = reinterpret_cast<const unsigned char*>(sv.rec) + (size_t)sv.task_off[task] * (VB_SEG_OWNERS * 2) + g * (M * 2);
+        chunk_t q[VB_SEG_PREFETCH];
+#pragma unroll
+        for (int i = 0; i < VB_SEG_PREFETCH; ++i) { q[i] = __ldcs(reinterpret_cast<const chunk_t*>(sp)); sp += VB_SEG_OWNERS * 2; }
+        const uint16_t* __restrict__ ns = sv.nsteps + (size_t)task * sv.n_win;
+        uint32_t n_next = ns[0];
+        int bi = 0;
+        uint32_t phase = 0;
+        const uint32_t lane_base = ring + (uint32_t)sub * 16;
+        for (int wd = 0; wd < sv.n_win; ++wd) {
+            const uint32_t n = n_next;
+            if (wd + 1 < sv.n_win) n_next = ns[wd + 1];
+            mbar_wait(bars + 8 * bi, phase);
+            const uint32_t base = lane_base + (uint32_t)bi * win_bytes;
+            for (uint32_t s = 0; s < n; ++s) {
+                const chunk_t c = q[0];
+#pragma unroll
+                for (int i = 0; i + 1 < VB_SEG_PREFETCH; ++i) q[i] = q[i + 1];
+                q[VB_SEG_PREFETCH - 1] = __ldcs(reinterpret_cast<const chunk_t*>(sp));
+                sp += VB_SEG_OWNERS * 2;
+                if constexpr (PREC == 0) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(&c);
+                    seg_step(u.x & 0xffffu, base, acc[0]); seg_step(u.x >> 16, base, acc[1]);
+                    seg_step(u.y & 0xffffu, base, acc[2]); seg_step(u.y >> 16, base, acc[3]);
+                    seg_step(u.z & 0xffffu, base, acc[4]); seg_step(u.z >> 16, base, acc[5]);
+                    seg_step(u.w & 0xffffu, base, acc[6]); seg_step(u.w >> 16, base, acc[7]);
+                } else {
+                    const uint2 u = *reinterpret_cast<const uint2*>(&c);
+                    seg_step(u.x & 0xffffu, base, acc[0]); seg_step(u.x >> 16, base, acc[1]);
+                    seg_step(u.y & 0xffffu, base, acc[2]); seg_step(u.y >> 16, base, acc[3]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 8 * (NB + bi));
+            if (++bi == NB) { bi = 0; phase ^= 1; }
+        }
+    }
+
+    // ---------------- epilogue: the LPO lanes of a slot hold NC columns each
+    const int K = p.K, KT = p.KT;
+    double r0 = 0.0, r1 = 0.0;                   // GM_CELL*: LB_p, KL_ID partial sums
+    double t1[VB_MAX_GT], t2[VB_MAX_GT];         // GM_SNP: theta partial sums (alternative / reference allele rows)
+#pragma unroll
+    for (int gq = 0; gq < VB_MAX_GT; ++gq) t1[gq] = t2[gq] = 0.0;
+    const double unq = PREC == 0 ? 1.0 : (sa.mode == GM_SNP ? 1.0 / 4294967296.0 : -1.0 / p.qscale[b]);
+
+    // the streaming task first, then a share of the tasks without records (accumulators are zero for those)
+    int64_t et = task;
+    int64_t extra = sv.n_task_stream + (int64_t)cta * NW + w;
+    if (w >= NW) { et = -1; extra = sv.n_task; }
+    for (;;) {
+        if (et < 0) {
+            if (extra >= sv.n_task) break;
+            et = extra;
+            extra += (int64_t)grid * NW;
+        }
+#pragma unroll
+        for (int mi = 0; mi < M; ++mi) {
+            const int owner = sv.perm[et * VB_SEG_OWNERS + g * M + mi];
+            double v[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) v[c] = PREC == 0 ? (double)acc[mi][c] : (double)acc[mi][c] * unq;
+            bool valid[NC], primary[NC];
+            int kk[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int col = NC * sub + c;
+                kk[c] = col % KT;
+                valid[c] = kk[c] < K && owner >= 0;
+                primary[c] = col < KT && valid[c];
+            }
+            if (sa.has_heavy && owner >= 0) {
+                const double* __restrict__ H = p.H + ((size_t)b * sv.n_owner + owner) * VB_ROW_DOUBLES + NC * sub;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) v[c] += H[c];
+            }
+            if (sa.mode == GM_CELL || sa.mode == GM_CELL_LL) {
+                const int64_t j = owner >= 0 ? owner : 0;
+                const size_t prow = (size_t)(p.id_rows == 1 ? 0 : j) * K;
+                double* __restrict__ R = p.R + ((size_t)b * p.C + j) * K;
+                double* __restrict__ LL = p.ll + ((size_t)b * p.C + j) * K;
+                double pr[NC];
+                if (sa.mode == GM_CELL) {
+                    double mx = -INFINITY;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        pr[c] = valid[c] ? v[c] + p.lidp[prow + kk[c]] : -INFINITY;
+                        mx = fmax(mx, pr[c]);
+                    }
+#pragma unroll
+                    for (int off = 1; off < LPO; off <<= 1) mx = fmax(mx, __shfl_xor_sync(VB_FULL, mx, off));
+                    double z = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        pr[c] = pr[c] == -INFINITY ? 0.0 : exp(pr[c] - mx);
+                        if (primary[c]) z += pr[c];
+                    }
+#pragma unroll
+                    for (int off = 1; off < LPO; off <<= 1) z += __shfl_xor_sync(VB_FULL, z, off);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) pr[c] = pr[c] / z;
+                    if (owner >= 0) {
+                        // 128-byte-row copy (columns replicated 16/KT times) for the SNP pass
+                        double* __restrict__ RP = p.RP + ((size_t)b * p.C + j) * VB_ROW_DOUBLES + NC * sub;
+#pragma unroll
+                        for (int c = 0; c < NC; c += 2) *reinterpret_cast<double2*>(RP + c) = make_double2(pr[c], pr[c + 1]);
+                        if constexpr (PREC == 1) {
+                            uint32_t* __restrict__ RQ = p.RPq + ((size_t)b * p.C + j) * VB_ROW_DOUBLES + NC * sub;
+                            *reinterpret_cast<uint4*>(RQ) = make_uint4(quant_unit(pr[0]), quant_unit(pr[1]), quant_unit(pr[2]), quant_unit(pr[3]));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) pr[c] = primary[c] ? R[kk[c]] : 0.0;
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    if (primary[c]) {
+                        const double a = v[c], pv = pr[c];
+                        LL[kk[c]] = a;
+                        if (sa.mode == GM_CELL) R[kk[c]] = pv;
+                        r0 += a * pv;
+                        if (pv > 0.0) r1 += pv * (log(pv) - p.lidp_kl[prow + kk[c]]);
+                    }
+                }
+            } else {   // GM_SNP
+                const int64_t i = owner >= 0 ? owner >> 1 : 0;
+                const int al = owner & 1;
+                const int G = p.G;
+                double* __restrict__ S = (al ? p.S1 : p.S2) + ((size_t)b * p.V + i) * K;
+                const double* __restrict__ GT = (do_theta && p.GT) ? p.GT + ((size_t)b * p.V + i) * K * G : nullptr;
+                double tt[VB_MAX_GT];
+#pragma unroll
+                for (int gq = 0; gq < VB_MAX_GT; ++gq) tt[gq] = 0.0;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    if (primary[c]) {
+                        S[kk[c]] = v[c];
+                        if (GT) {
+#pragma unroll
+                            for (int gq = 0; gq < VB_MAX_GT; ++gq)
+                                if (gq < G) tt[gq] += v[c] * GT[(size_t)kk[c] * G + gq];
+                        }
+                    }
+                }
+                if (do_theta && p.ase) {
+                    // theta per SNP (vireo_model.py:177 `axis=1`): the raw sums are parked in the ab rows
+#pragma unroll
+                    for (int gq = 0; gq < VB_MAX_GT; ++gq) {
+                        if (gq < G) {
+                            double u = tt[gq];
+#pragma unroll
+                            for (int off = 1; off < LPO; off <<= 1) u += __shfl_xor_sync(VB_FULL, u, off);
+                            if (sub == 0 && owner >= 0) p.ab[((size_t)b * p.T + i) * 2 * G + (al ? 0 : G) + gq] = u;
+                        }
+                    }
+                } else if (do_theta && owner >= 0) {
+#pragma unroll
+                    for (int gq = 0; gq < VB_MAX_GT; ++gq) { if (al) t1[gq] += tt[gq]; else t2[gq] += tt[gq]; }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc[i][c] = 0;
+        et = -1;
+    }
+
+    // ---------------- block-level partial sums (fixed geometry -> run-to-run identical)
+    const int nwt = NW + 1;
+    if (sa.mode == GM_CELL || sa.mode == GM_CELL_LL) {
+        r0 = warp_sum(r0);
+        r1 = warp_sum(r1);
+        if (lane == 0) { red[w * VB_SG_RED_DOUBLES] = r0; red[w * VB_SG_RED_DOUBLES + 1] = r1; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0.0, c = 0.0;
+            for (int i = 0; i < nwt; ++i) { a += red[i * VB_SG_RED_DOUBLES]; c += red[i * VB_SG_RED_DOUBLES + 1]; }
+            double* out = p.part + (size_t)b * p.part_stride + p.off_cell + 2 * blockIdx.x;
+            out[0] = a;
+            out[1] = c;
+        }
+    } else if (sa.mode == GM_SNP && do_theta && !p.ase) {
+#pragma unroll
+        for (int gq = 0; gq < VB_MAX_GT; ++gq) {
+            if (gq < p.G) {
+                const double u1 = warp_sum(t1[gq]), u2 = warp_sum(t2[gq]);
+                if (lane == 0) { red[w * VB_SG_RED_DOUBLES + gq] = u1; red[w * VB_SG_RED_DOUBLES + VB_MAX_GT + gq] = u2; }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * VB_MAX_GT) {
+            const int gq = threadIdx.x % VB_MAX_GT;
+            double t = 0.0;
+            if (gq < p.G)
+                for (int i = 0; i < nwt; ++i) t += red[i * VB_SG_RED_DOUBLES + threadIdx.x];
+            p.part[(size_t)b * p.part_stride + p.off_theta + (size_t)blockIdx.x * 2 * VB_MAX_GT + threadIdx.x] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: dispatch
+// ---------------------------------------------------------------------------------------------
+static SegView view_of_set(const SegSet& g) {
+    SegView v;
+    v.n_owner = g.n_owner; v.n_gather = g.n_gather; v.n_task = g.n_task; v.n_task_stream = g.n_task_stream;
+    v.n_win = g.n_win; v.win_rows = g.win_rows;
+    v.perm = g.perm; v.nsteps = g.nsteps; v.task_off = g.task_off; v.rec = g.rec;
+    v.hptr = g.hptr; v.hrow = g.hrow; v.hcnt = g.hcnt;
+    return v;
+}
+
+static size_t seg_smem(int prec, int nb, int win_rows) {
+    return (size_t)nb * win_rows * (prec == 0 ? 128 : 64) + 16 * 8 + (size_t)(VB_SEG_MAX_WARPS + 1) * VB_SG_RED_DOUBLES * 8;
+}
+
+static bool g_seg_attr_set = false;
+
+// ori 0: cell pass (table = p.Wt / p.Wq), ori 1: SNP pass (table = p.RP / p.RPq)
+int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, cudaStream_t st) {
+    const int prec = p.tiled == 3 ? 1 : 0;
+    const SegSet& g = ori ? m->sB[prec] : m->sA[prec];
+    if (!g.built) { vb_set_error("segment format was not built"); return VB_E_ARG; }
+    if (!g_seg_attr_set) {
+        VB_CUDA(cudaFuncSetAttribute(k_seg<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VB_CUDA(cudaFuncSetAttribute(k_seg<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        g_seg_attr_set = true;
+    }
+    const int nb = g.nb;
+    const size_t smem = seg_smem(prec, nb, g.win_rows);
+    if (smem > 227 * 1024) { vb_set_error("segment kernel: window buffers exceed shared memory"); return VB_E_ARG; }
+    const SegView sv = view_of_set(g);
+    SegArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.mode = mode; sa.theta_mode = theta_mode; sa.nb = nb;
+    const double* tab64 = ori ? p.RP : p.Wt;
+    if (prec == 0) { sa.table = reinterpret_cast<const unsigned char*>(tab64); sa.table_stride = g.n_gather * 128; }
+    else { sa.table = reinterpret_cast<const unsigned char*>(ori ? p.RPq : p.Wq); sa.table_stride = g.n_gather * 64; }
+    sa.has_heavy = g.n_heavy > 0;
+    int grid_x;
+    vb_seg_geometry(g, &grid_x, &sa.nwarps);
+    const int cls = ori ? 0 : 3;
+    if (sa.has_heavy) {
+        int64_t hb = (g.n_owner + VB_WARPS - 1) / VB_WARPS;
+        if (hb > (int64_t)m->sm_count * 8) hb = (int64_t)m->sm_count * 8;
+        if (hb < 1) hb = 1;
+        VB_LAUNCH(cls, st, k_seg_heavy<<<dim3((unsigned)hb, p.B), VB_THREADS, 0, st>>>(
+            g.n_owner, g.hptr, g.hrow, g.hcnt, tab64, g.n_gather * VB_ROW_DOUBLES, p.H, g.n_owner * VB_ROW_DOUBLES, p.ctrl));
+        VB_CUDA(cudaGetLastError());
+    }
+    const dim3 grid(grid_x, p.B);
+    const int threads = (sa.nwarps + 1) * 32;
+    VB_LAUNCH(cls, st, {
+        if (prec == 0) k_seg<0><<<grid, threads, smem, st>>>(sv, p, sa);
+        else k_seg<1><<<grid, threads, smem, st>>>(sv, p, sa);
+    });
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
+int vb_seg_quantise_rows(const vb_counts* m, const EmP& p, cudaStream_t st) {
+    const int64_t n = (int64_t)p.B * p.C * VB_ROW_DOUBLES;
+    int64_t nb = (n + VB_THREADS - 1) / VB_THREADS;
+    if (nb > (int64_t)m->sm_count * 8) nb = (int64_t)m->sm_count * 8;
+    if (nb < 1) nb = 1;
+    VB_LAUNCH(7, st, k_seg_quant_rows<<<(unsigned)nb, VB_THREADS, 0, st>>>(p.RP, n, p.RPq));
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}

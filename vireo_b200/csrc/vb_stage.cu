@@ -169,6 +169,7 @@ extern "C" void vb_counts_destroy(vb_counts* m) {
     cudaFree(m->cell_ptr); cudaFree(m->cell_idx); cudaFree(m->cell_cnt); cudaFree(m->cell_dp);
     cudaFree(m->snp_ptr); cudaFree(m->snp_idx); cudaFree(m->snp_cnt); cudaFree(m->snp_dp);
     vb_gather_free(m);
+    vb_seg_free(m);
     delete m;
 }
 
@@ -192,6 +193,18 @@ extern "C" int64_t vb_counts_info(const vb_counts* m, int what) {
         case 14: { int g = 0, w = 0; if (m->gA.built) vb_gather_geometry(m, m->gA, &g, &w); return g; }
         case 15: { int g = 0, w = 0; if (m->gB.built) vb_gather_geometry(m, m->gB, &g, &w); return g; }
         case 16: return m->gA.n_light;
+        // window-segment formats: 20 + 10 * precision + {0 built, 1 / 2 super-steps of the cell / SNP pass,
+        // 3 / 4 largest reads of one owner's stream (cell / SNP pass), 5 / 6 grid.x, 7 bytes, 8 residual pairs, 9 stream pairs}
+        case 20: case 30: { const int q = what >= 30; return m->sA[q].built && m->sB[q].built; }
+        case 21: case 31: return m->sA[what >= 30].n_step;
+        case 22: case 32: return m->sB[what >= 30].n_step;
+        case 23: case 33: return m->sA[what >= 30].max_reads;
+        case 24: case 34: return m->sB[what >= 30].max_reads;
+        case 25: case 35: return m->sA[what >= 30].grid;
+        case 26: case 36: return m->sB[what >= 30].grid;
+        case 27: case 37: return m->sA[what >= 30].bytes + m->sB[what >= 30].bytes;
+        case 28: case 38: return m->sA[what >= 30].n_heavy;
+        case 29: case 39: return m->sA[what >= 30].n_light;
         default: return -1;
     }
 }
