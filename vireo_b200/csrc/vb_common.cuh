@@ -92,7 +92,9 @@ struct GatherView {
 #define VB_SEG_CNT_BITS 5
 #define VB_SEG_MAX_COUNT 31
 #define VB_SEG_MAX_WIN_ROWS 2048
-#define VB_SEG_PREFETCH 3                 // super-steps of records in flight per warp
+#define VB_SEG_DEPTH64 4                  // super-steps of records in flight per warp, FP64 tables (8 B per lane each)
+#define VB_SEG_L2_AHEAD 4096              // bytes of the record stream requested into L2 ahead of the register queue
+#define VB_SEG_DEPTH32 4                  // same, fixed-point tables (8 B per lane each)
 
 struct SegSet {
     int built;
@@ -100,6 +102,7 @@ struct SegSet {
     int64_t n_task;          // ceil(n_owner / 32) tasks in sorted order (longest owners first)
     int64_t n_task_stream;   // the first n_task_stream tasks carry records; the rest only need the epilogue
     int n_win, win_rows, nb; // windows of the table, rows per window, windows resident in shared memory
+    int look;                // 1: a segment also carries pairs of the next window (look-ahead fill)
     int64_t n_step;          // super-steps in total
     int64_t n_light;         // pairs carried by the streams
     int64_t n_heavy;         // pairs in the residual
@@ -117,7 +120,7 @@ struct SegSet {
 
 struct SegView {
     int64_t n_owner, n_gather, n_task, n_task_stream;
-    int n_win, win_rows;
+    int n_win, win_rows, look;
     const int32_t* __restrict__ perm;
     const uint16_t* __restrict__ nsteps;
     const int64_t* __restrict__ task_off;

@@ -16,8 +16,11 @@
 //     32 stay in registers (static indexing: the slot index is the unrolled loop variable);
 //   * the table streams through NB window buffers; a producer warp refills a buffer when every
 //     consumer warp has released it (full/empty mbarriers), consumers wait per window, not per record;
-//   * the records of a task are stored per window as super-steps of 32 x 16 bits, prefetched from
-//     global memory VB_SEG_PREFETCH super-steps ahead;
+//   * the records of a task are stored per window as super-steps of 32 x 16 bits; a segment (the
+//     super-steps of one window) may also carry pairs of the NEXT window, which is resident as well,
+//     in the slots that lock-step would otherwise pad with null records (look-ahead fill: 59% -> 85%
+//     useful slots); segments are padded to groups of DEPTH super-steps so that the register queue
+//     that prefetches them DEPTH super-steps ahead needs no rotation;
 //   * PREC 1 keeps the table as unsigned 32-bit fixed point (rows of 64 bytes: half the crossbar and
 //     L2 traffic) and accumulates count * value exactly in 64-bit integers, so the result does not
 //     depend on the summation order; the quantisation error is bounded per owner by
@@ -107,21 +110,38 @@ __global__ void k_sg_wincount(const CountsView m, int64_t n_active, const int32_
     }
 }
 
-// super-steps of (task, window) = the largest pair count among the task's 32 owners
-__global__ void k_sg_taskmax(const uint16_t* __restrict__ cnt, int64_t n_active, int64_t n_task_stream, int n_win,
-                             uint16_t* __restrict__ nsteps, int64_t* __restrict__ wide) {
-    const int64_t n = n_task_stream * n_win;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e <= n; e += (int64_t)gridDim.x * blockDim.x) {
-        if (e == n) { wide[e] = 0; continue; }
-        const int64_t t = e / n_win;
-        const int w = (int)(e - t * n_win);
-        uint16_t mx = 0;
-        for (int s = 0; s < VB_SEG_OWNERS; ++s) {
-            const int64_t pos = t * VB_SEG_OWNERS + s;
-            if (pos < n_active) { const uint16_t c = cnt[(size_t)pos * n_win + w]; mx = c > mx ? c : mx; }
+// Segment plan, one thread per streaming task.  Segment w holds, for every owner slot, the owner's pairs of
+// window w that segment w-1 did not take, followed by up to `slack` pairs of window w+1 (look-ahead fill), where
+// slack = segment length - own pairs and the segment length is the largest own-pair count of the 32 owners.
+//   nsteps[t][w] super-steps of the segment, take[pos][w] pairs of window w+1 that owner `pos` serves in segment w,
+//   wide[t][w]   nsteps rounded up to a multiple of `depth` (stream positions)
+__global__ void k_sg_plan(const uint16_t* __restrict__ cnt, int64_t n_active, int64_t n_task_stream, int n_win, int look,
+                          int depth, uint16_t* __restrict__ nsteps, uint16_t* __restrict__ take, int64_t* __restrict__ wide) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t <= n_task_stream; t += (int64_t)gridDim.x * blockDim.x) {
+        if (t == n_task_stream) { wide[t * n_win] = 0; continue; }
+        uint16_t carry[VB_SEG_OWNERS];
+        for (int sl = 0; sl < VB_SEG_OWNERS; ++sl) carry[sl] = 0;
+        for (int w = 0; w < n_win; ++w) {
+            int n = 0;
+            for (int sl = 0; sl < VB_SEG_OWNERS; ++sl) {
+                const int64_t pos = t * VB_SEG_OWNERS + sl;
+                if (pos < n_active) { const int own = (int)cnt[(size_t)pos * n_win + w] - (int)carry[sl]; n = own > n ? own : n; }
+            }
+            for (int sl = 0; sl < VB_SEG_OWNERS; ++sl) {
+                const int64_t pos = t * VB_SEG_OWNERS + sl;
+                if (pos >= n_active) continue;
+                const int own = (int)cnt[(size_t)pos * n_win + w] - (int)carry[sl];
+                int tk = 0;
+                if (look && w + 1 < n_win) {
+                    const int nxt = cnt[(size_t)pos * n_win + w + 1];
+                    tk = n - own < nxt ? n - own : nxt;
+                }
+                take[(size_t)pos * n_win + w] = (uint16_t)tk;
+                carry[sl] = (uint16_t)tk;
+            }
+            nsteps[t * n_win + w] = (uint16_t)n;
+            wide[t * n_win + w] = (int64_t)((n + depth - 1) / depth) * depth;
         }
-        nsteps[e] = mx;
-        wide[e] = mx;
     }
 }
 
@@ -130,25 +150,59 @@ __global__ void k_sg_widen(const uint32_t* __restrict__ in, int64_t n, int64_t* 
         out[i] = i < n ? (int64_t)in[i] : 0;
 }
 
-// write the records and the residual CSR; one thread per sorted position
+// write the records and the residual CSR; one thread per sorted position.  Within window v the owner's first
+// take[v-1] pairs belong to segment v-1 (row offsets relative to window v-1, i.e. >= win_rows), the rest to segment v.
+// The order of an owner's records inside a segment is free.  With 64-byte table rows (`pair_dist` > 0) two owner
+// slots share one shared-memory wavefront (slots s and s + pair_dist of a super-step): rows of equal parity hit the
+// same 16 banks.  Slot s therefore lists its even rows from the front and its odd rows from the back of the segment,
+// slot s + pair_dist the other way round, so that most steps pair an even with an odd row.
 template <int ORI, bool WIDE>
 __global__ void k_sg_fill(const CountsView m, int64_t n_owner, int64_t n_active, const int32_t* __restrict__ perm, int win_rows,
-                          int n_win, const int64_t* __restrict__ step_off, uint16_t* __restrict__ rec,
+                          int n_win, int pair_dist, const int64_t* __restrict__ step_off, const uint16_t* __restrict__ cnt,
+                          const uint16_t* __restrict__ take, uint16_t* __restrict__ rec,
                           const int64_t* __restrict__ hptr, int32_t* __restrict__ hrow, uint32_t* __restrict__ hcnt) {
     for (int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pos < n_owner; pos += (int64_t)gridDim.x * blockDim.x) {
         const int64_t o = perm[pos];
         const bool streams = pos < n_active;
         const int64_t t = pos / VB_SEG_OWNERS;
         const int slot = (int)(pos % VB_SEG_OWNERS);
+        const uint32_t front_parity = (pair_dist > 0 && (slot & pair_dist)) ? 1u : 0u;    // row parity listed from the front
+        const uint16_t* crow = cnt + (size_t)pos * n_win;
+        const uint16_t* trow = take + (size_t)pos * n_win;
         int64_t h = hptr[o];
         int w = -1;
-        int64_t s = 0;
+        int k = 0;                 // index of the pair inside its window
+        int early = 0;             // pairs of window w served by segment w-1
+        // per segment: first super-step, records of this owner, cursors from the front and from the back
+        int64_t base_prev = 0, base_cur = 0;
+        int tot_prev = 0, tot_cur = 0, f_prev = 0, b_prev = 0, f_cur = 0, b_cur = 0;
         for_records<ORI, WIDE>(m, o, [&](int g, uint32_t c) {
             if (c > VB_SEG_MAX_COUNT || !streams) { hrow[h] = g; hcnt[h] = c; ++h; return; }
             const int gw = g / win_rows;
-            if (gw != w) { w = gw; s = step_off[t * n_win + w]; }
-            rec[(size_t)s * VB_SEG_OWNERS + slot] = (uint16_t)(((uint32_t)(g - gw * win_rows) << VB_SEG_CNT_BITS) | c);
-            ++s;
+            if (gw != w) {
+                if (gw == w + 1 && w >= 0) { base_prev = base_cur; tot_prev = tot_cur; f_prev = f_cur; b_prev = b_cur; }
+                else if (gw > 0) {      // the segment before gw holds only early pairs of this window (none of its own)
+                    base_prev = step_off[t * n_win + gw - 1];
+                    tot_prev = (int)crow[gw - 1] - (gw > 1 ? (int)trow[gw - 2] : 0) + (int)trow[gw - 1];
+                    f_prev = b_prev = 0;
+                }
+                w = gw; k = 0;
+                early = w > 0 ? trow[w - 1] : 0;
+                base_cur = step_off[t * n_win + w];
+                tot_cur = (int)crow[w] - early + (int)trow[w];
+                f_cur = b_cur = 0;
+            }
+            int64_t s;
+            uint32_t rel;
+            if (k < early) {
+                rel = (uint32_t)(g - (gw - 1) * win_rows);
+                s = pair_dist == 0 ? base_prev + f_prev++ : ((rel & 1u) == front_parity ? base_prev + f_prev++ : base_prev + tot_prev - 1 - b_prev++);
+            } else {
+                rel = (uint32_t)(g - gw * win_rows);
+                s = pair_dist == 0 ? base_cur + f_cur++ : ((rel & 1u) == front_parity ? base_cur + f_cur++ : base_cur + tot_cur - 1 - b_cur++);
+            }
+            rec[(size_t)s * VB_SEG_OWNERS + slot] = (uint16_t)((rel << VB_SEG_CNT_BITS) | c);
+            ++k;
         });
     }
 }
@@ -175,18 +229,23 @@ static int env_int(const char* name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 
-// window geometry per table precision: rows per window and resident windows (shared memory: nb * rows * row bytes)
-static void seg_window(int prec, int* win_rows, int* nb) {
-    if (prec == 0) { *win_rows = env_int("VIREO_B200_SEG_WR64", 768); *nb = env_int("VIREO_B200_SEG_NB64", 2); }
+// window geometry per table precision: rows per window and resident windows (shared memory: nb * rows * row bytes).
+// Look-ahead fill needs the windows w and w+1 resident while w+2 loads: nb >= 3.
+static void seg_window(int prec, int* win_rows, int* nb, int* look) {
+    if (prec == 0) { *win_rows = env_int("VIREO_B200_SEG_WR64", 512); *nb = env_int("VIREO_B200_SEG_NB64", 3); }
     else { *win_rows = env_int("VIREO_B200_SEG_WR32", 1024); *nb = env_int("VIREO_B200_SEG_NB32", 3); }
+    *look = env_int("VIREO_B200_SEG_LOOK", 1) ? 1 : 0;
     if (*win_rows < 32) *win_rows = 32;
-    if (*win_rows > VB_SEG_MAX_WIN_ROWS) *win_rows = VB_SEG_MAX_WIN_ROWS;
+    if (*win_rows > VB_SEG_MAX_WIN_ROWS / 2) *win_rows = VB_SEG_MAX_WIN_ROWS / 2;     // 11-bit row offsets span two windows
     *win_rows &= ~7;
     if (*nb < 2) *nb = 2;
     const int row_bytes = prec == 0 ? 128 : 64;
-    while ((size_t)*nb * *win_rows * row_bytes > 200 * 1024 && *nb > 2) --*nb;
+    while ((size_t)*nb * *win_rows * row_bytes > 200 * 1024 && *nb > 3) --*nb;
     while ((size_t)*nb * *win_rows * row_bytes > 200 * 1024) *win_rows -= 8;
+    if (*nb < 3) *look = 0;
 }
+
+static int seg_depth(int prec) { return prec == 0 ? VB_SEG_DEPTH64 : VB_SEG_DEPTH32; }
 
 template <int ORI>
 static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
@@ -195,8 +254,9 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
     const int64_t O = ORI == 0 ? m->C : 2 * m->V;
     const int64_t Gn = ORI == 0 ? 2 * m->V : m->C;
     if (O >= (1ll << 31) - 64 || Gn >= (1ll << 31) - 4096) { vb_set_error("segment format: more than 2^31 rows"); return VB_E_UNSUPPORTED; }
-    int win_rows, nb;
-    seg_window(prec, &win_rows, &nb);
+    int win_rows, nb, look;
+    seg_window(prec, &win_rows, &nb, &look);
+    const int depth = seg_depth(prec);
     int n_win = (int)((Gn + win_rows - 1) / win_rows);
     if (n_win < 1) n_win = 1;
     const int64_t n_task = (O + VB_SEG_OWNERS - 1) / VB_SEG_OWNERS;
@@ -257,7 +317,7 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
         VB_CUDA(cudaMemcpyAsync(hsums, sums, sizeof(hsums), cudaMemcpyDeviceToHost, st));
         VB_CUDA(cudaStreamSynchronize(st));
     }
-    g.n_owner = O; g.n_gather = Gn; g.n_task = n_task; g.n_win = n_win; g.win_rows = win_rows; g.nb = nb;
+    g.n_owner = O; g.n_gather = Gn; g.n_task = n_task; g.n_win = n_win; g.win_rows = win_rows; g.nb = nb; g.look = look;
     g.n_light = (int64_t)hsums[0]; g.n_heavy = (int64_t)hsums[1]; g.max_reads = (int64_t)hsums[2];
     g.n_task_stream = (n_active + VB_SEG_OWNERS - 1) / VB_SEG_OWNERS;
     const int64_t nts = g.n_task_stream;
@@ -268,20 +328,22 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
 
     // super-steps per (task, window) and their offsets
     const int64_t n_tw = nts * n_win;
-    uint16_t* cnt_ow;
+    uint16_t *cnt_ow, *take;
     int64_t *wide, *step_off;
-    if ((rc = tmp.alloc(&cnt_ow, (size_t)(n_active ? n_active : 1) * n_win)) || (rc = tmp.alloc(&wide, n_tw + 1)) ||
+    const size_t n_cw = (size_t)(n_active ? n_active : 1) * n_win;
+    if ((rc = tmp.alloc(&cnt_ow, n_cw)) || (rc = tmp.alloc(&take, n_cw)) || (rc = tmp.alloc(&wide, n_tw + 1)) ||
         (rc = tmp.alloc(&step_off, n_tw + 1)))
         return rc;
     VB_CUDA(cudaMalloc(&g.nsteps, (n_tw ? n_tw : 1) * sizeof(uint16_t)));
     VB_CUDA(cudaMalloc(&g.task_off, (nts + 1) * sizeof(int64_t)));
-    VB_CUDA(cudaMemsetAsync(cnt_ow, 0, (size_t)(n_active ? n_active : 1) * n_win * sizeof(uint16_t), st));
+    VB_CUDA(cudaMemsetAsync(cnt_ow, 0, n_cw * sizeof(uint16_t), st));
+    VB_CUDA(cudaMemsetAsync(take, 0, n_cw * sizeof(uint16_t), st));
     if (n_active) {
         if (m->wide) k_sg_wincount<ORI, true><<<grid1d(n_active, sm), 256, 0, st>>>(v, n_active, g.perm, win_rows, n_win, cnt_ow);
         else k_sg_wincount<ORI, false><<<grid1d(n_active, sm), 256, 0, st>>>(v, n_active, g.perm, win_rows, n_win, cnt_ow);
         VB_CUDA(cudaGetLastError());
     }
-    k_sg_taskmax<<<grid1d(n_tw + 1, sm), 256, 0, st>>>(cnt_ow, n_active, nts, n_win, g.nsteps, wide);
+    k_sg_plan<<<grid1d(nts + 1, sm), 64, 0, st>>>(cnt_ow, n_active, nts, n_win, look, depth, g.nsteps, take, wide);
     VB_CUDA(cudaGetLastError());
     {
         size_t tb = 0;
@@ -312,12 +374,13 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
         if ((rc = tmp.alloc((unsigned char**)&cub_tmp, tb))) return rc;
         VB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, hw, g.hptr, O + 1, st));
     }
-    const size_t n_rec = ((size_t)total_steps + VB_SEG_PREFETCH + 1) * VB_SEG_OWNERS;   // slack: the prefetch runs ahead
+    // slack: the register queue runs `depth` super-steps ahead, the L2 prefetch VB_SEG_L2_AHEAD bytes
+    const size_t n_rec = ((size_t)total_steps + 2 * depth) * VB_SEG_OWNERS + VB_SEG_L2_AHEAD / 2 + 64;
     VB_CUDA(cudaMalloc(&g.rec, n_rec * sizeof(uint16_t)));
     VB_CUDA(cudaMemsetAsync(g.rec, 0, n_rec * sizeof(uint16_t), st));
     if (O) {
-        if (m->wide) k_sg_fill<ORI, true><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, win_rows, n_win, step_off, g.rec, g.hptr, g.hrow, g.hcnt);
-        else k_sg_fill<ORI, false><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, win_rows, n_win, step_off, g.rec, g.hptr, g.hrow, g.hcnt);
+        if (m->wide) k_sg_fill<ORI, true><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, win_rows, n_win, prec == 1 ? 4 : 0, step_off, cnt_ow, take, g.rec, g.hptr, g.hrow, g.hcnt);
+        else k_sg_fill<ORI, false><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, win_rows, n_win, prec == 1 ? 4 : 0, step_off, cnt_ow, take, g.rec, g.hptr, g.hrow, g.hcnt);
         VB_CUDA(cudaGetLastError());
     }
     VB_CUDA(cudaStreamSynchronize(st));
@@ -383,9 +446,10 @@ k_seg_heavy(int64_t n_owner, const int64_t* __restrict__ hptr, const int32_t* __
     }
 }
 
-// ID_prob rows [B*C, 16] -> unsigned 32-bit fixed point (value * 2^32, saturated)
+// ID_prob rows [B*C, 16] -> unsigned 32-bit fixed point, value * (2^32 - 1): a posterior of exactly 1.0 (most
+// cells once the fit has settled) is represented exactly, so the per-SNP sums carry no systematic bias
 __device__ __forceinline__ uint32_t quant_unit(double r) {
-    const double s = r * 4294967296.0;
+    const double s = r * 4294967295.0;
     return s >= 4294967295.0 ? 0xffffffffu : (s > 0.0 ? (uint32_t)__double2ull_rn(s) : 0u);
 }
 
@@ -411,34 +475,98 @@ struct SegArgs {
 };
 
 template <int PREC> struct SegCfg;
-template <> struct SegCfg<0> { static constexpr int LPO = 8, NC = 2, ROWB = 128, ROW_SHIFT = 2; };
-template <> struct SegCfg<1> { static constexpr int LPO = 4, NC = 4, ROWB = 64, ROW_SHIFT = 1; };
+template <> struct SegCfg<0> { static constexpr int LPO = 4, NC = 4, ROWB = 128; };
+template <> struct SegCfg<1> { static constexpr int LPO = 4, NC = 4, ROWB = 64; };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// one owner slot of one super-step: PREC 0
-__device__ __forceinline__ void seg_step(uint32_t r, uint32_t base, double (&a)[2]) {
-    const uint32_t c = r & VB_SEG_MAX_COUNT;
-    if (c) {
-        double vx, vy;
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(base + ((r & 0xffe0u) << 2)));
-        const double d = (double)(int)c;
-        a[0] = fma(d, vx, a[0]);
-        a[1] = fma(d, vy, a[1]);
-    }
+// One owner slot of one super-step.  `w` holds two 16-bit records; HI selects the upper one.  The row offset
+// (bits 15..5 of the record) times the row size gives the byte offset from the start of window w's buffer; a
+// record of the look-ahead window lands in the next buffer, which is contiguous unless the ring wraps (WRAP).
+// FP64 tables: 4 lanes x 4 columns, two 16-byte loads per lane.
+struct SegScratch64 { double v[2][4]; };     // landing registers of the FP64 loads, two sets in flight
+struct SegScratch32 {};
+
+template <bool HI, bool WRAP>
+__device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes, double (&a)[4],
+                                         double (&v)[4]) {
+    const uint32_t c = HI ? (w & 0x001f0000u) : (w & 0x1fu);
+    uint32_t t;
+    asm("and.b32 %0, %1, %2;" : "=r"(t) : "r"(w), "r"(HI ? 0xffe00000u : 0xffe0u));   // opaque: keeps the scaling one LEA
+    uint32_t off = HI ? __umulhi(t, 1u << 18) : t * 4u;    // row offset * 128 bytes
+    if (WRAP && off >= wrap_at) off -= ring_bytes;
+    const uint32_t addr = base + off;
+    // `base` points at this lane's 16-byte granule in one half of the row; the other half is 64 bytes away (even
+    // lane groups start in the lower half, odd groups in the upper half: the two rows that share a wavefront never
+    // meet in a bank).
+    // count -> double without the conversion pipe: 2^52 + x is exact, subtracting 2^52 leaves x.  The upper record of
+    // a word is used in place (count << 16): odd slots carry a factor 2^16 that the epilogue removes.
+    const double d = __hiloint2double(0x43300000, (int)c) - 4503599627370496.0;
+    // Predicated loads, unconditional FMAs: a null record (count 0) issues no shared-memory wavefront, keeps
+    // whatever finite table values its landing registers held, and adds 0 * value.  (An `if` around loads and
+    // FMAs is compiled to a branch, which serialises consecutive slots on the load latency.)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %4, 0;\n\t"
+        "@p ld.shared.v2.f64 {%0, %1}, [%5];\n\t"
+        "@p ld.shared.v2.f64 {%2, %3}, [%6];\n\t}"
+        : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3])
+        : "r"(c), "r"(addr), "r"(addr ^ 64u));
+    a[0] = fma(d, v[0], a[0]);
+    a[1] = fma(d, v[1], a[1]);
+    a[2] = fma(d, v[2], a[2]);
+    a[3] = fma(d, v[3], a[3]);
 }
-// PREC 1: exact integer accumulation of count * fixed-point value
-__device__ __forceinline__ void seg_step(uint32_t r, uint32_t base, unsigned long long (&a)[4]) {
-    const uint32_t c = r & VB_SEG_MAX_COUNT;
+// Fixed point: exact integer accumulation of count * value.  The upper record of a word is used in place
+// (count << 16, row offset << 16): the accumulators of odd slots carry a factor 2^16 that the epilogue removes
+// (safe while the reads of one owner stay below 2^16, checked when the format is built).
+template <bool HI, bool WRAP>
+__device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes, unsigned long long (&a)[4]) {
+    const uint32_t c = HI ? (w & 0x001f0000u) : (w & 0x1fu);
+    // the address does not depend on the null test: keeping it outside shortens the dependent chain in front of the load
+    uint32_t t;
+    asm("and.b32 %0, %1, %2;" : "=r"(t) : "r"(w), "r"(HI ? 0xffe00000u : 0xffe0u));
+    uint32_t off = HI ? __umulhi(t, 1u << 17) : t * 2u;    // row offset * 64 bytes
+    if (WRAP && off >= wrap_at) off -= ring_bytes;
+    const uint32_t addr = base + off;
     if (c) {
         uint32_t v0, v1, v2, v3;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(base + ((r & 0xffe0u) << 1)));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
         a[0] += (unsigned long long)c * v0;
         a[1] += (unsigned long long)c * v1;
         a[2] += (unsigned long long)c * v2;
         a[3] += (unsigned long long)c * v3;
+    }
+}
+
+template <bool WRAP>
+__device__ __forceinline__ void seg_super_step(const uint2& u, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes, double (&acc)[4][4],
+                                               SegScratch64& sc) {
+    seg_step<false, WRAP>(u.x, base, wrap_at, ring_bytes, acc[0], sc.v[0]); seg_step<true, WRAP>(u.x, base, wrap_at, ring_bytes, acc[1], sc.v[1]);
+    seg_step<false, WRAP>(u.y, base, wrap_at, ring_bytes, acc[2], sc.v[0]); seg_step<true, WRAP>(u.y, base, wrap_at, ring_bytes, acc[3], sc.v[1]);
+}
+template <bool WRAP>
+__device__ __forceinline__ void seg_super_step(const uint2& u, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes,
+                                               unsigned long long (&acc)[4][4], SegScratch32&) {
+    seg_step<false, WRAP>(u.x, base, wrap_at, ring_bytes, acc[0]); seg_step<true, WRAP>(u.x, base, wrap_at, ring_bytes, acc[1]);
+    seg_step<false, WRAP>(u.y, base, wrap_at, ring_bytes, acc[2]); seg_step<true, WRAP>(u.y, base, wrap_at, ring_bytes, acc[3]);
+}
+
+// the super-steps of one segment; the queue q holds the next DEPTH super-steps of the stream
+template <bool WRAP, int DEPTH, typename chunk_t, typename acc_t, typename scratch_t>
+__device__ __forceinline__ void seg_segment(uint32_t n, chunk_t (&q)[DEPTH], const unsigned char*& sp, uint32_t base, uint32_t wrap_at,
+                                            uint32_t ring_bytes, acc_t& acc, scratch_t& sc) {
+    for (uint32_t s = 0; s < n; s += DEPTH) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + VB_SEG_L2_AHEAD));
+#pragma unroll
+        for (int i = 0; i < DEPTH; ++i) {
+            const chunk_t c = q[i];
+            q[i] = __ldcs(reinterpret_cast<const chunk_t*>(sp + i * (VB_SEG_OWNERS * 2)));
+            if (s + i < n) seg_super_step<WRAP>(c, base, wrap_at, ring_bytes, acc, sc);
+        }
+        sp += DEPTH * (VB_SEG_OWNERS * 2);
     }
 }
 
@@ -448,7 +576,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     using Cfg = SegCfg<PREC>;
     constexpr int LPO = Cfg::LPO, M = Cfg::LPO, NC = Cfg::NC, ROWB = Cfg::ROWB;
     typedef typename std::conditional<PREC == 0, double, unsigned long long>::type acc_t;
-    typedef typename std::conditional<PREC == 0, uint4, uint2>::type chunk_t;
+    typedef uint2 chunk_t;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int b = blockIdx.y;
     if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
@@ -511,41 +639,41 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
         }
     } else if (task >= 0) {
         // ---------------- consumer warp: 32 owner slots, LPO lanes per slot
+        constexpr int DEPTH = PREC == 0 ? VB_SEG_DEPTH64 : VB_SEG_DEPTH32;
         const unsigned char* sp = reinterpret_cast<const unsigned char*>(sv.rec) + (size_t)sv.task_off[task] * (VB_SEG_OWNERS * 2) + g * (M * 2);
-        chunk_t q[VB_SEG_PREFETCH];
+        typename std::conditional<PREC == 0, SegScratch64, SegScratch32>::type sc;
+        if constexpr (PREC == 0) {
 #pragma unroll
-        for (int i = 0; i < VB_SEG_PREFETCH; ++i) { q[i] = __ldcs(reinterpret_cast<const chunk_t*>(sp)); sp += VB_SEG_OWNERS * 2; }
+            for (int i = 0; i < 8; ++i) sc.v[i >> 2][i & 3] = 0.0;
+        }
+        chunk_t q[DEPTH];
+#pragma unroll
+        for (int i = 0; i < DEPTH; ++i) q[i] = __ldcs(reinterpret_cast<const chunk_t*>(sp + i * (VB_SEG_OWNERS * 2)));
+        sp += DEPTH * (VB_SEG_OWNERS * 2);
         const uint16_t* __restrict__ ns = sv.nsteps + (size_t)task * sv.n_win;
         uint32_t n_next = ns[0];
-        int bi = 0;
-        uint32_t phase = 0;
-        const uint32_t lane_base = ring + (uint32_t)sub * 16;
+        int bi = 0;                          // buffer of window wd
+        uint32_t phase = 0;                  // its fill parity
+        // FP64 rows: odd lane groups read the upper half of a row first (see seg_step)
+        const uint32_t lane_base = ring + (uint32_t)sub * 16 + (PREC == 0 ? (uint32_t)(g & 1) * 64 : 0u);
+        const uint32_t ring_bytes = (uint32_t)NB * win_bytes;
+        const int look = sv.look;
+        if (look) mbar_wait(bars, 0);        // window 0; every segment then waits for the window after its own
         for (int wd = 0; wd < sv.n_win; ++wd) {
             const uint32_t n = n_next;
             if (wd + 1 < sv.n_win) n_next = ns[wd + 1];
-            mbar_wait(bars + 8 * bi, phase);
-            const uint32_t base = lane_base + (uint32_t)bi * win_bytes;
-            for (uint32_t s = 0; s < n; ++s) {
-                const chunk_t c = q[0];
-#pragma unroll
-                for (int i = 0; i + 1 < VB_SEG_PREFETCH; ++i) q[i] = q[i + 1];
-                q[VB_SEG_PREFETCH - 1] = __ldcs(reinterpret_cast<const chunk_t*>(sp));
-                sp += VB_SEG_OWNERS * 2;
-                if constexpr (PREC == 0) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(&c);
-                    seg_step(u.x & 0xffffu, base, acc[0]); seg_step(u.x >> 16, base, acc[1]);
-                    seg_step(u.y & 0xffffu, base, acc[2]); seg_step(u.y >> 16, base, acc[3]);
-                    seg_step(u.z & 0xffffu, base, acc[4]); seg_step(u.z >> 16, base, acc[5]);
-                    seg_step(u.w & 0xffffu, base, acc[6]); seg_step(u.w >> 16, base, acc[7]);
-                } else {
-                    const uint2 u = *reinterpret_cast<const uint2*>(&c);
-                    seg_step(u.x & 0xffffu, base, acc[0]); seg_step(u.x >> 16, base, acc[1]);
-                    seg_step(u.y & 0xffffu, base, acc[2]); seg_step(u.y >> 16, base, acc[3]);
-                }
+            const bool last_buf = bi + 1 == NB;
+            if (look) {
+                if (wd + 1 < sv.n_win) mbar_wait(bars + 8 * (last_buf ? 0 : bi + 1), last_buf ? phase ^ 1 : phase);
+            } else {
+                mbar_wait(bars + 8 * bi, phase);
             }
+            const uint32_t base = lane_base + (uint32_t)bi * win_bytes;
+            if (look && last_buf) seg_segment<true, DEPTH>(n, q, sp, base, win_bytes, ring_bytes, acc, sc);
+            else seg_segment<false, DEPTH>(n, q, sp, base, win_bytes, ring_bytes, acc, sc);
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + 8 * (NB + bi));
-            if (++bi == NB) { bi = 0; phase ^= 1; }
+            if (last_buf) { bi = 0; phase ^= 1; } else ++bi;
         }
     }
 
@@ -555,7 +683,13 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     double t1[VB_MAX_GT], t2[VB_MAX_GT];         // GM_SNP: theta partial sums (alternative / reference allele rows)
 #pragma unroll
     for (int gq = 0; gq < VB_MAX_GT; ++gq) t1[gq] = t2[gq] = 0.0;
-    const double unq = PREC == 0 ? 1.0 : (sa.mode == GM_SNP ? 1.0 / 4294967296.0 : -1.0 / p.qscale[b]);
+    // columns of this lane: [col0, col0 + 1] and [col0 + col2, col0 + col2 + 1]
+    //   fixed point: four consecutive columns;  FP64: one granule in each half of the row, the first from the half
+    //   this lane group reads first
+    const int col0 = PREC == 0 ? 2 * sub + 8 * (g & 1) : 4 * sub;
+    const int col2 = PREC == 0 ? ((g & 1) ? -8 : 8) : 2;
+    const double unq = PREC == 0 ? 1.0 : (sa.mode == GM_SNP ? 1.0 / 4294967295.0 : -1.0 / p.qscale[b]);
+    const double unq_hi = unq / 65536.0;     // odd slots accumulate count << 16 (exact power of two in either precision)
 
     // the streaming task first, then a share of the tasks without records (accumulators are zero for those)
     int64_t et = task;
@@ -572,20 +706,20 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
             const int owner = sv.perm[et * VB_SEG_OWNERS + g * M + mi];
             double v[NC];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) v[c] = PREC == 0 ? (double)acc[mi][c] : (double)acc[mi][c] * unq;
+            for (int c = 0; c < NC; ++c) v[c] = (double)acc[mi][c] * ((mi & 1) ? unq_hi : unq);
             bool valid[NC], primary[NC];
             int kk[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                const int col = NC * sub + c;
+                const int col = col0 + (c < 2 ? c : col2 + c - 2);
                 kk[c] = col % KT;
                 valid[c] = kk[c] < K && owner >= 0;
                 primary[c] = col < KT && valid[c];
             }
             if (sa.has_heavy && owner >= 0) {
-                const double* __restrict__ H = p.H + ((size_t)b * sv.n_owner + owner) * VB_ROW_DOUBLES + NC * sub;
+                const double* __restrict__ H = p.H + ((size_t)b * sv.n_owner + owner) * VB_ROW_DOUBLES + col0;
 #pragma unroll
-                for (int c = 0; c < NC; ++c) v[c] += H[c];
+                for (int c = 0; c < NC; ++c) v[c] += H[c < 2 ? c : col2 + c - 2];
             }
             if (sa.mode == GM_CELL || sa.mode == GM_CELL_LL) {
                 const int64_t j = owner >= 0 ? owner : 0;
@@ -614,11 +748,11 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
                     for (int c = 0; c < NC; ++c) pr[c] = pr[c] / z;
                     if (owner >= 0) {
                         // 128-byte-row copy (columns replicated 16/KT times) for the SNP pass
-                        double* __restrict__ RP = p.RP + ((size_t)b * p.C + j) * VB_ROW_DOUBLES + NC * sub;
-#pragma unroll
-                        for (int c = 0; c < NC; c += 2) *reinterpret_cast<double2*>(RP + c) = make_double2(pr[c], pr[c + 1]);
+                        double* __restrict__ RP = p.RP + ((size_t)b * p.C + j) * VB_ROW_DOUBLES + col0;
+                        *reinterpret_cast<double2*>(RP) = make_double2(pr[0], pr[1]);
+                        *reinterpret_cast<double2*>(RP + col2) = make_double2(pr[2], pr[3]);
                         if constexpr (PREC == 1) {
-                            uint32_t* __restrict__ RQ = p.RPq + ((size_t)b * p.C + j) * VB_ROW_DOUBLES + NC * sub;
+                            uint32_t* __restrict__ RQ = p.RPq + ((size_t)b * p.C + j) * VB_ROW_DOUBLES + col0;
                             *reinterpret_cast<uint4*>(RQ) = make_uint4(quant_unit(pr[0]), quant_unit(pr[1]), quant_unit(pr[2]), quant_unit(pr[3]));
                         }
                     }
@@ -719,7 +853,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
 static SegView view_of_set(const SegSet& g) {
     SegView v;
     v.n_owner = g.n_owner; v.n_gather = g.n_gather; v.n_task = g.n_task; v.n_task_stream = g.n_task_stream;
-    v.n_win = g.n_win; v.win_rows = g.win_rows;
+    v.n_win = g.n_win; v.win_rows = g.win_rows; v.look = g.look;
     v.perm = g.perm; v.nsteps = g.nsteps; v.task_off = g.task_off; v.rec = g.rec;
     v.hptr = g.hptr; v.hrow = g.hrow; v.hcnt = g.hcnt;
     return v;
