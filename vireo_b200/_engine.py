@@ -200,6 +200,27 @@ def _dev(arr, device):
     return t.from_numpy(a).to("cuda:%d" % device)
 
 
+_PINNED_UP = {}
+
+
+def _stage_up(shape, device, fill):
+    """Host -> device through a reused pinned buffer: `fill(view)` writes the float64 payload straight into the
+    pinned staging area (one host pass instead of a temporary plus a pageable copy), then one DMA."""
+    t = torch()
+    n = int(np.prod(shape))
+    buf = _PINNED_UP.get(n)
+    if buf is None:
+        if len(_PINNED_UP) > 16:
+            _PINNED_UP.clear()
+        buf = t.empty(max(n, 1), dtype=t.float64, pin_memory=True)
+        _PINNED_UP[n] = buf
+    fill(buf.numpy()[:n].reshape(shape))
+    out = t.empty(max(n, 1), dtype=t.float64, device="cuda:%d" % device)
+    out[:n].copy_(buf[:n], non_blocking=True)
+    t.cuda.current_stream(device).synchronize()      # the staging buffer is reused by the next upload
+    return out
+
+
 def _zeros(n, device, dtype=None):
     t = torch()
     return t.zeros(int(max(n, 1)), dtype=dtype or t.float64, device="cuda:%d" % device)
@@ -299,10 +320,10 @@ class VireoBatch:
         t = torch()
 
         def stack(name, shape):
-            out = np.empty((B,) + shape, dtype=np.float64)
-            for i, m in enumerate(self.models):
-                out[i] = np.broadcast_to(np.asarray(getattr(m, name), dtype=np.float64), shape)
-            return _dev(out, dev)
+            def fill(out):
+                for i, m in enumerate(self.models):
+                    out[i] = np.broadcast_to(np.asarray(getattr(m, name), dtype=np.float64), shape)
+            return _stage_up((B,) + shape, dev, fill)
 
         self.id_prob = stack("ID_prob", (C_, K))
         self.gt_prob = stack("GT_prob", (V, K, G))
@@ -317,8 +338,15 @@ class VireoBatch:
             raise ValueError("ID_prior shape %r does not broadcast to (%d, %d)" % (id_prior.shape, C_, K))
         self.id_rows = id_prior.shape[0]
         self.lidp, self.lidp_kl = _log_prior_pair(id_prior, dev)
-        gt_prior = np.broadcast_to(np.asarray(m0.GT_prior, dtype=np.float64), (V, K, G))
-        self.lgtp, self.lgtp_kl = _log_prior_pair(gt_prior, dev)
+        gt_prior = np.asarray(m0.GT_prior, dtype=np.float64)
+        flat = np.broadcast_to(gt_prior, (V, K, G)).reshape(V * K, G)
+        if V * K > 1 and (flat == flat[:1]).all():
+            # one genotype prior for every (SNP, donor) -- the default: logs of one row, replicated on the device
+            raw, norm = _log_prior_pair(flat[:1], dev)
+            self.lgtp = raw.view(1, G).expand(V * K, G).contiguous().view(-1)
+            self.lgtp_kl = norm.view(1, G).expand(V * K, G).contiguous().view(-1)
+        else:
+            self.lgtp, self.lgtp_kl = _log_prior_pair(flat, dev)
         s1p = np.asarray(m0.theta_s1_prior, dtype=np.float64).reshape(-1, G)
         s2p = np.asarray(m0.theta_s2_prior, dtype=np.float64).reshape(-1, G)
         if s1p.shape[0] not in (1, T):

@@ -103,6 +103,7 @@ struct SegSet {
     int64_t n_task_stream;   // the first n_task_stream tasks carry records; the rest only need the epilogue
     int n_win, win_rows, nb; // windows of the table, rows per window, windows resident in shared memory
     int look;                // 1: a segment also carries pairs of the next window (look-ahead fill)
+    int depth;               // super-steps per group of the record queue (segments are padded to a multiple)
     int64_t n_step;          // super-steps in total
     int64_t n_light;         // pairs carried by the streams
     int64_t n_heavy;         // pairs in the residual

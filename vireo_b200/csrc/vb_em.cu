@@ -770,7 +770,7 @@ static int launch_snp(const vb_counts* m, const EmP& p, int theta_mode, cudaStre
 // ---------------------------------------------------------------------------------------------
 // path selection: rows (v1, one warp per row, L2 gathers) or gather (vb_gather.cu, ring-slab streams)
 // ---------------------------------------------------------------------------------------------
-static int g_path = 0;                       // 0 auto, 1 rows, 2 gather, 3 segments (FP64 tables), 4 segments (fixed-point tables)
+static int g_path = 0;                       // 0 auto, 1 rows, 2 gather streams, 3 segments (FP64 tables), 4 segments (fixed-point tables)
 #define VB_GATHER_MIN_NNZ (4ll << 20)        // below this the passes are launch/latency bound either way
 
 extern "C" void vb_set_path(int mode) { g_path = mode < 0 || mode > 4 ? 0 : mode; }
@@ -782,20 +782,30 @@ static int want_gather(const vb_counts* mc, int K, int fixed_ok, int* use) {
     *use = 0;
     if (g_path == 1 || K > VB_ROW_DOUBLES) return VB_OK;
     if (g_path == 3 || g_path == 4) {
-        const int prec = (g_path == 4 && fixed_ok) ? 1 : 0;
-        const int rc = vb_seg_build(m, prec, 0);
+        int prec = (g_path == 4 && fixed_ok) ? 1 : 0;
+        int rc = vb_seg_build(m, prec, 0);
         if (rc) return rc;
+        // the fixed-point kernel keeps odd slots scaled by 2^16: one owner's stream may carry fewer than 2^16 reads
+        if (prec == 1 && (m->sA[1].max_reads >= 65536 || m->sB[1].max_reads >= 65536)) {
+            prec = 0;
+            if ((rc = vb_seg_build(m, 0, 0))) return rc;
+        }
         *use = 2 + prec;
         return VB_OK;
     }
-    if (g_path == 0 && (m->N < VB_GATHER_MIN_NNZ || m->gather_failed)) return VB_OK;
-    const int rc = vb_gather_build(m, 0);
-    if (rc) return g_path == 2 ? rc : VB_OK;
     if (g_path == 0) {
-        // mostly large counts (e.g. mitochondrial clone data): the residual kernel would do all the work
-        const int64_t pairs = m->gA.n_light + m->gA.n_heavy;
-        if (m->gA.n_heavy * 4 > pairs) return VB_OK;
+        // automatic: the window-segment kernels with FP64 tables for large count matrices; row kernels when the
+        // passes are launch/latency bound anyway, or when most pairs carry large counts (e.g. mitochondrial clone
+        // data) and the residual kernel would do all the work
+        if (m->N < VB_GATHER_MIN_NNZ || m->seg_failed[0]) return VB_OK;
+        if (vb_seg_build(m, 0, 0)) return VB_OK;
+        const int64_t pairs = m->sA[0].n_light + m->sA[0].n_heavy;
+        if (m->sA[0].n_heavy * 4 > pairs) return VB_OK;
+        *use = 2;
+        return VB_OK;
     }
+    const int rc = vb_gather_build(m, 0);      // g_path == 2
+    if (rc) return rc;
     *use = 1;
     return VB_OK;
 }

@@ -245,7 +245,10 @@ static void seg_window(int prec, int* win_rows, int* nb, int* look) {
     if (*nb < 3) *look = 0;
 }
 
-static int seg_depth(int prec) { return prec == 0 ? VB_SEG_DEPTH64 : VB_SEG_DEPTH32; }
+static int seg_depth(int prec) {
+    const int d = env_int(prec == 0 ? "VIREO_B200_SEG_DEPTH64" : "VIREO_B200_SEG_DEPTH32", prec == 0 ? VB_SEG_DEPTH64 : VB_SEG_DEPTH32);
+    return d >= 8 ? 8 : 4;
+}
 
 template <int ORI>
 static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
@@ -317,7 +320,7 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
         VB_CUDA(cudaMemcpyAsync(hsums, sums, sizeof(hsums), cudaMemcpyDeviceToHost, st));
         VB_CUDA(cudaStreamSynchronize(st));
     }
-    g.n_owner = O; g.n_gather = Gn; g.n_task = n_task; g.n_win = n_win; g.win_rows = win_rows; g.nb = nb; g.look = look;
+    g.n_owner = O; g.n_gather = Gn; g.n_task = n_task; g.n_win = n_win; g.win_rows = win_rows; g.nb = nb; g.look = look; g.depth = depth;
     g.n_light = (int64_t)hsums[0]; g.n_heavy = (int64_t)hsums[1]; g.max_reads = (int64_t)hsums[2];
     g.n_task_stream = (n_active + VB_SEG_OWNERS - 1) / VB_SEG_OWNERS;
     const int64_t nts = g.n_task_stream;
@@ -470,6 +473,7 @@ struct SegArgs {
     int nwarps;          // consumer warps per CTA (block size = (nwarps + 1) * 32)
     int nb;              // resident windows
     int has_heavy;       // add p.H[owner] before the epilogue
+    int wait_hint_ns;    // > 0: suspend-time hint of the window waits
     int64_t table_stride;    // bytes per restart of the gather table
     const unsigned char* table;
 };
@@ -570,7 +574,17 @@ __device__ __forceinline__ void seg_segment(uint32_t n, chunk_t (&q)[DEPTH], con
     }
 }
 
-template <int PREC>
+// wait for a phase of a window barrier; with a suspend-time hint a waiting warp stays off the issue slots longer
+__device__ __forceinline__ void seg_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    if (hint_ns == 0) { mbar_wait(bar, parity); return; }
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+    } while (!ok);
+}
+
+template <int PREC, int DEPTH>
 __global__ void __launch_bounds__((VB_SEG_MAX_WARPS + 1) * 32, 1)
 k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     using Cfg = SegCfg<PREC>;
@@ -639,7 +653,6 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
         }
     } else if (task >= 0) {
         // ---------------- consumer warp: 32 owner slots, LPO lanes per slot
-        constexpr int DEPTH = PREC == 0 ? VB_SEG_DEPTH64 : VB_SEG_DEPTH32;
         const unsigned char* sp = reinterpret_cast<const unsigned char*>(sv.rec) + (size_t)sv.task_off[task] * (VB_SEG_OWNERS * 2) + g * (M * 2);
         typename std::conditional<PREC == 0, SegScratch64, SegScratch32>::type sc;
         if constexpr (PREC == 0) {
@@ -658,15 +671,16 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
         const uint32_t lane_base = ring + (uint32_t)sub * 16 + (PREC == 0 ? (uint32_t)(g & 1) * 64 : 0u);
         const uint32_t ring_bytes = (uint32_t)NB * win_bytes;
         const int look = sv.look;
-        if (look) mbar_wait(bars, 0);        // window 0; every segment then waits for the window after its own
+        const uint32_t hint = (uint32_t)sa.wait_hint_ns;
+        if (look) seg_wait(bars, 0, hint);   // window 0; every segment then waits for the window after its own
         for (int wd = 0; wd < sv.n_win; ++wd) {
             const uint32_t n = n_next;
             if (wd + 1 < sv.n_win) n_next = ns[wd + 1];
             const bool last_buf = bi + 1 == NB;
             if (look) {
-                if (wd + 1 < sv.n_win) mbar_wait(bars + 8 * (last_buf ? 0 : bi + 1), last_buf ? phase ^ 1 : phase);
+                if (wd + 1 < sv.n_win) seg_wait(bars + 8 * (last_buf ? 0 : bi + 1), last_buf ? phase ^ 1 : phase, hint);
             } else {
-                mbar_wait(bars + 8 * bi, phase);
+                seg_wait(bars + 8 * bi, phase, hint);
             }
             const uint32_t base = lane_base + (uint32_t)bi * win_bytes;
             if (look && last_buf) seg_segment<true, DEPTH>(n, q, sp, base, win_bytes, ring_bytes, acc, sc);
@@ -871,8 +885,10 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
     const SegSet& g = ori ? m->sB[prec] : m->sA[prec];
     if (!g.built) { vb_set_error("segment format was not built"); return VB_E_ARG; }
     if (!g_seg_attr_set) {
-        VB_CUDA(cudaFuncSetAttribute(k_seg<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        VB_CUDA(cudaFuncSetAttribute(k_seg<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VB_CUDA(cudaFuncSetAttribute(k_seg<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VB_CUDA(cudaFuncSetAttribute(k_seg<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VB_CUDA(cudaFuncSetAttribute(k_seg<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VB_CUDA(cudaFuncSetAttribute(k_seg<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         g_seg_attr_set = true;
     }
     const int nb = g.nb;
@@ -886,6 +902,8 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
     if (prec == 0) { sa.table = reinterpret_cast<const unsigned char*>(tab64); sa.table_stride = g.n_gather * 128; }
     else { sa.table = reinterpret_cast<const unsigned char*>(ori ? p.RPq : p.Wq); sa.table_stride = g.n_gather * 64; }
     sa.has_heavy = g.n_heavy > 0;
+    static const int wait_hint = env_int("VIREO_B200_SEG_WAIT_NS", 0);
+    sa.wait_hint_ns = wait_hint;
     int grid_x;
     vb_seg_geometry(g, &grid_x, &sa.nwarps);
     const int cls = ori ? 0 : 3;
@@ -900,8 +918,10 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
     const dim3 grid(grid_x, p.B);
     const int threads = (sa.nwarps + 1) * 32;
     VB_LAUNCH(cls, st, {
-        if (prec == 0) k_seg<0><<<grid, threads, smem, st>>>(sv, p, sa);
-        else k_seg<1><<<grid, threads, smem, st>>>(sv, p, sa);
+        if (prec == 0 && g.depth == 4) k_seg<0, 4><<<grid, threads, smem, st>>>(sv, p, sa);
+        else if (prec == 0) k_seg<0, 8><<<grid, threads, smem, st>>>(sv, p, sa);
+        else if (g.depth == 4) k_seg<1, 4><<<grid, threads, smem, st>>>(sv, p, sa);
+        else k_seg<1, 8><<<grid, threads, smem, st>>>(sv, p, sa);
     });
     VB_CUDA(cudaGetLastError());
     return VB_OK;
