@@ -563,7 +563,10 @@ template <bool WRAP, int DEPTH, typename chunk_t, typename acc_t, typename scrat
 __device__ __forceinline__ void seg_segment(uint32_t n, chunk_t (&q)[DEPTH], const unsigned char*& sp, uint32_t base, uint32_t wrap_at,
                                             uint32_t ring_bytes, acc_t& acc, scratch_t& sc) {
     for (uint32_t s = 0; s < n; s += DEPTH) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + VB_SEG_L2_AHEAD));
+        // a group consumes DEPTH * 64 bytes of the warp's stream: one L2 prefetch per 128-byte line of it
+#pragma unroll
+        for (int l = 0; l < DEPTH * (VB_SEG_OWNERS * 2); l += 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + VB_SEG_L2_AHEAD + l));
 #pragma unroll
         for (int i = 0; i < DEPTH; ++i) {
             const chunk_t c = q[i];
