@@ -75,7 +75,9 @@ void vb_counts_destroy(vb_counts* m);
  * 6 grid.x of the cell pass (rows path), 7 grid.x of the SNP pass (rows path), 8 grid.x of the elementwise
  * (V*K) kernels, 9 gather-stream formats built, 10 / 11 stream records of the cell / SNP pass, 12 residual
  * (count >= 32) pairs, 13 bytes of the gather formats, 14 / 15 grid.x of the gather cell / SNP pass,
- * 16 pairs carried by the streams */
+ * 16 pairs carried by the streams; window-segment formats: 20 + 10 * precision (0 FP64, 1 fixed point) +
+ * {0 built, 1 / 2 super-steps of the cell / SNP pass, 3 / 4 largest reads of one row's stream (cell / SNP pass;
+ * fixed-point error bound = reads * 2^-33 * table range), 5 / 6 grid.x, 7 bytes, 8 residual pairs, 9 stream pairs} */
 int64_t vb_counts_info(const vb_counts* m, int what);
 
 /* sum over nnz(DP>0) of float32(min(log C(dp, ad), 700)), accumulated in float64.
@@ -86,7 +88,7 @@ int vb_binom_const(const vb_counts* m, double* scratch, double* out_host, void* 
 /* Sizes of the per-call workspaces, in elements, for a batch of B restarts. */
 typedef struct vb_ws_sizes {
     int64_t S;        /* doubles: S1 and S2, each [B, n_var, K]                 */
-    int64_t W;        /* doubles: per-allele tables [B, n_var, 2, K] (gather path: K -> 16) */
+    int64_t W;        /* doubles: per-allele tables [B, n_var, 2, K] (gather / segment paths: K -> 16; + fixed-point copy) */
     int64_t loglik;   /* doubles: [B, n_cell, K]                               */
     int64_t ab;       /* doubles: [B, T, 2*G] digamma differences              */
     int64_t part;     /* doubles: block partial sums                           */
@@ -193,9 +195,12 @@ void vb_launch_counts(int64_t* n8);
 void vb_profile_enable(int on);
 int vb_profile_read(double* ms8, int64_t* n8);
 
-/* Kernel family for the two sparse passes: 0 = automatic (gather-stream kernels for large count matrices
- * with n_donor <= 16, row kernels otherwise), 1 = row kernels (one warp per row, table gathered from L2),
- * 2 = gather-stream kernels (lane per row, table streamed through shared memory by bulk async copies).
+/* Kernel family for the two sparse passes: 0 = automatic (window-segment kernels with FP64 tables for large
+ * count matrices with n_donor <= 16, row kernels otherwise), 1 = row kernels (one warp per row, table gathered
+ * from L2), 2 = gather-stream kernels (lane per row, table streamed through a shared-memory ring),
+ * 3 = window-segment kernels, FP64 tables (4 lanes per row, table windows in shared memory),
+ * 4 = window-segment kernels with 32-bit fixed-point tables and exact 64-bit integer accumulation (Vireo
+ *     without ASE mode; < 1e-7 per update on log-likelihoods; other models use 3).
  * Process-wide; affects workspaces sized afterwards. */
 void vb_set_path(int mode);
 
