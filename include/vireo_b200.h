@@ -49,6 +49,9 @@ extern "C" {
 #define VB_PH_ID         8   /* logLik_ID (cell-major pass) + ID_prob softmax                         */
 #define VB_PH_ELBO      16   /* ELBO from the current state and the logLik_ID buffer                  */
 #define VB_PH_LOGLIK    32   /* logLik_ID only: fill the buffer, do not touch ID_prob                 */
+#define VB_PH_THETA_SUMS 64  /* recompute the theta update's sums over S1*GT, S2*GT from the S1/S2 buffers
+                              * (cell-sharded fit: VB_PH_SNP alone, all-reduce S1/S2 across devices, then this
+                              * together with VB_PH_THETA / GT / ID / ELBO)                           */
 
 #define VB_MAX_GT        8   /* largest n_GT the theta kernels hold in registers                      */
 #define VB_MAX_DONOR   256   /* largest n_donor of the fused cell kernel (32 lanes x 8 registers)     */

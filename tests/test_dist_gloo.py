@@ -75,3 +75,24 @@ def test_single_process_degenerates():
     final = np.array([1.0, 3.0, 2.0])
     out_final, best, state = vd.gather_restarts(final, {1: {"x": np.ones(2)}}, ["x"])
     assert np.array_equal(out_final, final) and best == 1 and np.array_equal(state["x"], np.ones(2))
+
+
+def test_cell_shard_bounds_and_convergence_rule():
+    """Host logic of the cell-sharded fit (vireo_b200/sharded.py): nnz-balanced contiguous shards, and the
+    reference's stopping rule (vireo_model.py:266-274) evaluated on the host from the all-reduced ELBO."""
+    sys.path.insert(0, ROOT)
+    from vireo_b200.sharded import cell_shards, converged
+    rng = np.random.RandomState(0)
+    nnz = rng.randint(0, 50, size=1000)
+    indptr = np.concatenate([[0], np.cumsum(nnz)])
+    for n in (1, 2, 3, 8):
+        b = cell_shards(indptr, n)
+        assert b[0] == 0 and b[-1] == 1000 and len(b) == n + 1 and (np.diff(b) >= 0).all()
+        per = np.diff(indptr[b])
+        assert per.sum() == indptr[-1] and per.max() - per.min() <= 2 * nnz.max()
+    assert list(cell_shards(np.zeros(5, dtype=np.int64), 2)) in ([0, 0, 4], [0, 4, 4])     # no reads at all
+    elbo = np.array([-10.0, -5.0, -4.0, -3.999, -3.9985, -3.9984])
+    assert not converged(elbo, 2, 2, 6, 1e-2, False)            # it must exceed min_iter (strict)
+    assert converged(elbo, 3, 2, 6, 1e-2, False)                # gain 0.001 < eps
+    assert not converged(elbo, 5, 2, 6, 1e-2, False)            # last iteration only warns
+    assert not converged(np.array([0.0, -1.0, -2.0, -3.0]), 3, 1, 10, 1e-2, False)   # a decrease only warns

@@ -356,7 +356,8 @@ class VireoBatch:
 
         ws = _lib.WsSizes()
         _lib.check(_lib.load().vb_vireo_ws_sizes(counts.handle, K, G, B, int(self.ase), C.byref(ws)))
-        self.S1, self.S2 = _zeros(ws.S, dev), _zeros(ws.S, dev)
+        self.S12 = _zeros(2 * ws.S, dev)          # S1 | S2 in one allocation: the cell-sharded fit all-reduces both at once
+        self.S1, self.S2 = self.S12[:ws.S], self.S12[ws.S:]
         self.W = _zeros(ws.W, dev)
         self.loglik = _zeros(ws.loglik, dev)
         self.ab = _zeros(ws.ab, dev)

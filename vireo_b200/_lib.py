@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvireo_b200.so")
 
 VB_I32, VB_I64, VB_F32, VB_F64 = 0, 1, 2, 3
-PH_SNP, PH_THETA, PH_GT, PH_ID, PH_ELBO, PH_LOGLIK = 1, 2, 4, 8, 16, 32
+PH_SNP, PH_THETA, PH_GT, PH_ID, PH_ELBO, PH_LOGLIK, PH_THETA_SUMS = 1, 2, 4, 8, 16, 32, 64
 MAX_GT, MAX_DONOR = 8, 256
 CTRL_N, SCAL_N = 4, 8
 

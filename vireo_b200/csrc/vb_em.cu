@@ -430,6 +430,66 @@ __global__ void __launch_bounds__(VB_THREADS) k_theta_ase(const EmP p, const int
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_theta_sums: the partial sums sum_{i,k} S1*GT_old, S2*GT_old of the theta update (vireo_model.py:175-181)
+// recomputed from S1/S2 -- for callers that reduce S1/S2 across devices after the SNP pass (cell-sharded fit) and
+// therefore cannot use the sums the SNP pass folds into its epilogue.  Same output layout as k_snp.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VB_THREADS) k_theta_sums(const EmP p) {
+    const int b = blockIdx.y;
+    const int K = p.K, G = p.G;
+    const int64_t VK = p.V * K;
+    const double* __restrict__ GT = p.GT + (size_t)b * VK * G;
+    const double* __restrict__ S1 = p.S1 + (size_t)b * VK;
+    const double* __restrict__ S2 = p.S2 + (size_t)b * VK;
+    if (p.ase) {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.V; i += (int64_t)gridDim.x * blockDim.x) {
+            double* row = p.ab + ((size_t)b * p.T + i) * 2 * G;
+            for (int g = 0; g < G; ++g) {
+                double u1 = 0.0, u2 = 0.0;
+                for (int k = 0; k < K; ++k) {
+                    const double gt = GT[((size_t)i * K + k) * G + g];
+                    u1 += S1[i * K + k] * gt;
+                    u2 += S2[i * K + k] * gt;
+                }
+                row[g] = u1;
+                row[G + g] = u2;
+            }
+        }
+        return;
+    }
+    double t1[VB_MAX_GT], t2[VB_MAX_GT];
+#pragma unroll
+    for (int g = 0; g < VB_MAX_GT; ++g) t1[g] = t2[g] = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < VK; e += (int64_t)gridDim.x * blockDim.x) {
+        const double s1 = S1[e], s2 = S2[e];
+#pragma unroll
+        for (int g = 0; g < VB_MAX_GT; ++g)
+            if (g < G) {
+                const double gt = GT[(size_t)e * G + g];
+                t1[g] += s1 * gt;
+                t2[g] += s2 * gt;
+            }
+    }
+    __shared__ double sh[VB_WARPS][2 * VB_MAX_GT];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+#pragma unroll
+    for (int g = 0; g < VB_MAX_GT; ++g) {
+        if (g < G) {
+            const double u1 = warp_sum(t1[g]), u2 = warp_sum(t2[g]);
+            if (lane == 0) { sh[wib][g] = u1; sh[wib][VB_MAX_GT + g] = u2; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * VB_MAX_GT) {
+        const int g = threadIdx.x % VB_MAX_GT;
+        double t = 0.0;
+        if (g < G)
+            for (int w = 0; w < VB_WARPS; ++w) t += sh[w][threadIdx.x];
+        p.part[(size_t)b * p.part_stride + p.off_theta + (size_t)blockIdx.x * 2 * VB_MAX_GT + threadIdx.x] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_gt: one thread per (SNP, donor)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(VB_THREADS) k_gt(const EmP p, const int do_gt) {
@@ -814,7 +874,7 @@ static int kt_for(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : 16); }
 
 static void part_layout(const vb_counts* m, EmP& p) {
     int ga = 0, gb = 0, nw;
-    int cap_snp = m->grid_snp, cap_cell = m->grid_cell;
+    int cap_snp = m->grid_snp > m->grid_elem ? m->grid_snp : m->grid_elem, cap_cell = m->grid_cell;
     if (m->gA.built) {
         vb_gather_geometry(m, m->gA, &ga, &nw); vb_gather_geometry(m, m->gB, &gb, &nw);
         if (ga > cap_cell) cap_cell = ga;
@@ -953,9 +1013,16 @@ static int vireo_iteration(const vb_counts* m, const EmP& p, int phases, bool in
     const int theta_mode = in_loop ? 2 : ((phases & VB_PH_THETA) ? 1 : 0);
     if (phases & VB_PH_SNP)
         if ((rc = launch_snp(m, p, theta_mode, st))) return rc;
+    if (!in_loop && phases == VB_PH_SNP) return VB_OK;      // S1/S2 only (the caller reduces them across devices)
+    EmP q = p;
+    if (!in_loop && (phases & VB_PH_THETA_SUMS)) {
+        VB_LAUNCH(0, st, k_theta_sums<<<elem, VB_THREADS, 0, st>>>(p));
+        VB_CUDA(cudaGetLastError());
+        q.n_snpblk = m->grid_elem;                           // k_theta sums this kernel's block partials
+    }
     // k_theta always runs: the digamma tables and KL_theta depend on the current beta_mu / beta_sum
-    if (p.ase) VB_LAUNCH(1, st, k_theta_ase<<<elem, VB_THREADS, 0, st>>>(p, theta_mode));
-    else VB_LAUNCH(1, st, k_theta<<<one, 2 * VB_MAX_GT * 32, 0, st>>>(p, theta_mode));
+    if (p.ase) VB_LAUNCH(1, st, k_theta_ase<<<elem, VB_THREADS, 0, st>>>(q, theta_mode));
+    else VB_LAUNCH(1, st, k_theta<<<one, 2 * VB_MAX_GT * 32, 0, st>>>(q, theta_mode));
     VB_CUDA(cudaGetLastError());
     const int do_gt = in_loop ? p.learn_gt : ((phases & VB_PH_GT) ? 1 : 0);
     VB_LAUNCH(2, st, k_gt<<<elem, VB_THREADS, 0, st>>>(p, do_gt));

@@ -10,6 +10,8 @@ and ignored.
 """
 import sys
 
+import os
+
 import numpy as np
 
 from . import _engine
@@ -98,7 +100,13 @@ def vireo_wrap(AD, DP, GT_prior=None, n_donor=None, learn_GT=True, n_init=20,
         modelCA.ELBO_ = np.atleast_1d(state["ELBO_"])
 
     if n_extra_donor == 0:
-        modelCA.fit(counts, None, min_iter=5, verbose=False)
+        if ws > 1 and os.environ.get("VIREO_B200_SHARD_CELLS", "0") == "1" and not modelCA.ASE_mode \
+                and not isinstance(AD, _engine.StagedCounts):
+            # the one fit restart sharding cannot spread: data-parallel over cells, one all-reduce per iteration
+            from .sharded import fit_cell_sharded
+            fit_cell_sharded(modelCA, AD, DP, min_iter=5, verbose=False)
+        else:
+            modelCA.fit(counts, None, min_iter=5, verbose=False)
     else:
         _ID_prob = donor_select(modelCA.GT_prob, modelCA.ID_prob, n_donor, mode=extra_donor_mode)
         modelCA = Vireo(n_var=n_var, n_cell=n_cell, n_donor=n_donor, learn_GT=learn_GT,
