@@ -543,7 +543,7 @@ class BmmBatch:
 # doublet pass
 # ---------------------------------------------------------------------------------------------
 
-def doublet_pass(counts, GT_prob, beta_mu, beta_sum, log_prior_both, ase):
+def doublet_pass(counts, GT_prob, beta_mu, beta_sum, log_prior_both, ase, want_loglik=False):
     """logLik over singlet + donor-pair columns, softmax with the doublet prior, LLR -- all on the device."""
     dev = counts.device
     V, K, G = GT_prob.shape
@@ -558,4 +558,5 @@ def doublet_pass(counts, GT_prob, beta_mu, beta_sum, log_prior_both, ase):
                                                 _ptr(lpd), lp.shape[0], _ptr(W), _ptr(ll), _ptr(pr),
                                                 _ptr(llr), _stream(dev)))
     C_ = counts.n_cell
-    return (ll.cpu().numpy().reshape(C_, K2), pr.cpu().numpy().reshape(C_, K2), llr.cpu().numpy())
+    # the log-likelihoods stay on the device (109 MB at cfg3; no caller reads them): posterior and LLR only
+    return (None if not want_loglik else _to_host(ll).reshape(C_, K2), _to_host(pr).reshape(C_, K2), _to_host(llr))

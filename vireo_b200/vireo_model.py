@@ -60,13 +60,13 @@ class Vireo():
         self.theta_s1_prior = beta_mu_prior * beta_sum_prior
         self.theta_s2_prior = (1 - beta_mu_prior) * beta_sum_prior
 
-        if ID_prior is None:
-            self.ID_prior = normalize(np.ones(self.ID_prob.shape))
+        if ID_prior is None:      # normalize(np.ones(shape)) of the reference, without the two passes over the array
+            self.ID_prior = np.full(self.ID_prob.shape, 1.0 / self.ID_prob.shape[-1])
         else:
             self.ID_prior = ID_prior[np.newaxis, :] if ID_prior.ndim == 1 else ID_prior
 
         if GT_prior is None:
-            self.GT_prior = normalize(np.ones(self.GT_prob.shape))
+            self.GT_prior = np.full(self.GT_prob.shape, 1.0 / self.GT_prob.shape[-1])
         else:
             if GT_prior.ndim == 2:
                 GT_prior = GT_prior[np.newaxis, :, :]
