@@ -150,10 +150,11 @@ struct vb_counts {
     GatherSet gA;           // cell pass
     GatherSet gB;           // SNP pass
     int gather_failed;      // a build attempt failed (message in vb_last_error); rows path is used
-    // window-segment formats (vb_seg.cu), index = table precision (0 FP64 rows of 128 B, 1 fixed-point rows of 64 B)
-    SegSet sA[2];           // cell pass
-    SegSet sB[2];           // SNP pass
-    int seg_failed[2];
+    // window-segment formats (vb_seg.cu), index = table kind: 0 FP64 rows of 128 B (16 columns), 1 fixed-point rows
+    // of 64 B (16 columns), 2 FP64 rows of 64 B (8 columns, n_donor <= 8)
+    SegSet sA[3];           // cell pass
+    SegSet sB[3];           // SNP pass
+    int seg_failed[3];
 };
 
 // vb_gather.cu
@@ -191,6 +192,7 @@ struct EmP {
     int* ctrl;
     // gather path (vb_gather.cu): Wt is then [B, 2V, 16] (rows of 128 bytes, columns replicated 16/KT times),
     // RP the same layout of ID_prob [B, C, 16], H the residual sums [B, max(C, 2V), 16]
+    int RW;                    // doubles per row of the padded tables (Wt, RP, H): 16, or 8 for the narrow FP64 segment kernels
     int tiled, KT;             // tiled: 0 row kernels, 1 gather-stream kernels, 2 window-segment kernels (FP64 tables),
                                //        3 window-segment kernels (32-bit fixed-point tables)
     double *RP, *H;
@@ -291,7 +293,7 @@ void vb_launch_end(int cls, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1);
 void vb_gather_geometry(const vb_counts* m, const GatherSet& g, int* grid, int* nwarps);
 int vb_gather_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, double* plain_out,
                      cudaStream_t st);
-int vb_pad_rows_launch(const vb_counts* m, const double* src, int64_t n_row, int K, int KT, int B, double* dst,
+int vb_pad_rows_launch(const vb_counts* m, const double* src, int64_t n_row, int K, int KT, int RW, int B, double* dst,
                        cudaStream_t st);
 enum { GM_CELL = 0, GM_CELL_LL = 1, GM_SNP = 2, GM_PLAIN = 3 };
 // vb_seg.cu

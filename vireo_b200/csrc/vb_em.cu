@@ -17,6 +17,7 @@
 // k_bmm_theta in place of k_theta + k_gt.
 //
 // All reductions are two-stage with a fixed launch geometry, so results are run-to-run identical.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -539,8 +540,8 @@ __global__ void __launch_bounds__(VB_THREADS) k_gt(const EmP p, const int do_gt)
             }
         if (p.tiled) {
             // gather-table rows of 128 bytes, columns replicated 16/KT times (vb_gather.cu)
-            double* w0 = p.Wt + ((size_t)b * p.V + i) * 2 * VB_ROW_DOUBLES;
-            for (int c = k; c < VB_ROW_DOUBLES; c += p.KT) { w0[c] = wb; w0[VB_ROW_DOUBLES + c] = wa; }
+            double* w0 = p.Wt + ((size_t)b * p.V + i) * 2 * p.RW;
+            for (int c = k; c < p.RW; c += p.KT) { w0[c] = wb; w0[p.RW + c] = wa; }
             if (p.tiled == 3) {
                 const double qs = p.qscale[b];
                 const double fb = -wb * qs, fa = -wa * qs;
@@ -575,8 +576,8 @@ __global__ void __launch_bounds__(VB_THREADS) k_bmm_theta(const EmP p, const int
         const int64_t i = e / p.K;
         const int k = (int)(e - i * p.K);
         if (p.tiled) {
-            double* w0 = p.Wt + ((size_t)b * p.V + i) * 2 * VB_ROW_DOUBLES;
-            for (int c = k; c < VB_ROW_DOUBLES; c += p.KT) { w0[c] = t.B; w0[VB_ROW_DOUBLES + c] = t.A; }
+            double* w0 = p.Wt + ((size_t)b * p.V + i) * 2 * p.RW;
+            for (int c = k; c < p.RW; c += p.KT) { w0[c] = t.B; w0[p.RW + c] = t.A; }
         } else {
             double* wt = p.Wt + (size_t)b * VK * 2 + (size_t)i * 2 * p.K + k;
             wt[0] = t.B;
@@ -837,30 +838,39 @@ extern "C" void vb_set_path(int mode) { g_path = mode < 0 || mode > 4 ? 0 : mode
 
 // *use = kernel family serving this (counts, K): 0 rows, 1 gather streams, 2 window segments with FP64 tables,
 // 3 window segments with fixed-point tables (`fixed_ok`: the caller can build them); builds the formats on first use
+static int kt_for(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : 16); }
+
+// narrow FP64 rows (8 doubles = 64 bytes) serve n_donor <= 8; VIREO_B200_SEG_NARROW=0 keeps the 16-column rows
+static bool seg_narrow_ok(int K) {
+    static const bool on = !(getenv("VIREO_B200_SEG_NARROW") && atoi(getenv("VIREO_B200_SEG_NARROW")) == 0);
+    return on && kt_for(K) <= 8;
+}
+
 static int want_gather(const vb_counts* mc, int K, int fixed_ok, int* use) {
     vb_counts* m = const_cast<vb_counts*>(mc);
     *use = 0;
     if (g_path == 1 || K > VB_ROW_DOUBLES) return VB_OK;
+    const int fp64_fmt = seg_narrow_ok(K) ? 2 : 0;      // FP64 tables: 64-byte rows when 8 columns are enough
     if (g_path == 3 || g_path == 4) {
-        int prec = (g_path == 4 && fixed_ok) ? 1 : 0;
+        int prec = (g_path == 4 && fixed_ok) ? 1 : fp64_fmt;
         int rc = vb_seg_build(m, prec, 0);
         if (rc) return rc;
         // the fixed-point kernel keeps odd slots scaled by 2^16: one owner's stream may carry fewer than 2^16 reads
         if (prec == 1 && (m->sA[1].max_reads >= 65536 || m->sB[1].max_reads >= 65536)) {
-            prec = 0;
-            if ((rc = vb_seg_build(m, 0, 0))) return rc;
+            prec = fp64_fmt;
+            if ((rc = vb_seg_build(m, prec, 0))) return rc;
         }
-        *use = 2 + prec;
+        *use = prec == 1 ? 3 : 2;
         return VB_OK;
     }
     if (g_path == 0) {
         // automatic: the window-segment kernels with FP64 tables for large count matrices; row kernels when the
         // passes are launch/latency bound anyway, or when most pairs carry large counts (e.g. mitochondrial clone
         // data) and the residual kernel would do all the work
-        if (m->N < VB_GATHER_MIN_NNZ || m->seg_failed[0]) return VB_OK;
-        if (vb_seg_build(m, 0, 0)) return VB_OK;
-        const int64_t pairs = m->sA[0].n_light + m->sA[0].n_heavy;
-        if (m->sA[0].n_heavy * 4 > pairs) return VB_OK;
+        if (m->N < VB_GATHER_MIN_NNZ || m->seg_failed[fp64_fmt]) return VB_OK;
+        if (vb_seg_build(m, fp64_fmt, 0)) return VB_OK;
+        const int64_t pairs = m->sA[fp64_fmt].n_light + m->sA[fp64_fmt].n_heavy;
+        if (m->sA[fp64_fmt].n_heavy * 4 > pairs) return VB_OK;
         *use = 2;
         return VB_OK;
     }
@@ -870,8 +880,6 @@ static int want_gather(const vb_counts* mc, int K, int fixed_ok, int* use) {
     return VB_OK;
 }
 
-static int kt_for(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : 16); }
-
 static void part_layout(const vb_counts* m, EmP& p) {
     int ga = 0, gb = 0, nw;
     int cap_snp = m->grid_snp > m->grid_elem ? m->grid_snp : m->grid_elem, cap_cell = m->grid_cell;
@@ -880,16 +888,17 @@ static void part_layout(const vb_counts* m, EmP& p) {
         if (ga > cap_cell) cap_cell = ga;
         if (gb > cap_snp) cap_snp = gb;
     }
-    int sa[2] = {0, 0}, sb[2] = {0, 0};
-    for (int q = 0; q < 2; ++q)
+    int sa[3] = {0, 0, 0}, sb[3] = {0, 0, 0};
+    for (int q = 0; q < 3; ++q)
         if (m->sA[q].built && m->sB[q].built) {
             vb_seg_geometry(m->sA[q], &sa[q], &nw); vb_seg_geometry(m->sB[q], &sb[q], &nw);
             if (sa[q] > cap_cell) cap_cell = sa[q];
             if (sb[q] > cap_snp) cap_snp = sb[q];
         }
-    p.n_snpblk = p.tiled >= 2 ? sb[p.tiled - 2] : (p.tiled ? gb : m->grid_snp);
+    const int fmt = p.tiled == 3 ? 1 : (p.RW == 8 ? 2 : 0);
+    p.n_snpblk = p.tiled >= 2 ? sb[fmt] : (p.tiled ? gb : m->grid_snp);
     p.n_elemblk = m->grid_elem;
-    p.n_cellblk = p.tiled >= 2 ? sa[p.tiled - 2] : (p.tiled ? ga : m->grid_cell);
+    p.n_cellblk = p.tiled >= 2 ? sa[fmt] : (p.tiled ? ga : m->grid_cell);
     p.n_klth = (p.bmm || p.ase) ? m->grid_elem : 1;
     p.off_theta = 0;
     p.off_klgt = p.off_theta + cap_snp * 2 * VB_MAX_GT;
@@ -924,6 +933,7 @@ static int fill_vireo(const vb_counts* m, const vb_vireo_args* a, EmP& p) {
         const int rc = want_gather(m, p.K, !p.ase, &use);
         if (rc) return rc;
         p.tiled = use; p.KT = kt_for(p.K); p.RP = a->rpad; p.H = a->heavy;
+        p.RW = (use == 2 && seg_narrow_ok(p.K)) ? 8 : VB_ROW_DOUBLES;
         if (use && (!p.RP || !p.H)) { vb_set_error("rpad / heavy workspace is NULL (see vb_vireo_ws_sizes)"); return VB_E_ARG; }
         if (use == 3) {   // fixed-point copies live behind the FP64 tables of the same workspaces
             p.Wq = reinterpret_cast<uint32_t*>(p.Wt + (size_t)p.B * p.V * 2 * VB_ROW_DOUBLES);
@@ -963,6 +973,7 @@ static int fill_bmm(const vb_counts* m, const vb_bmm_args* a, EmP& p) {
         const int rc = want_gather(m, p.K, 0, &use);
         if (rc) return rc;
         p.tiled = use; p.KT = kt_for(p.K); p.RP = a->rpad; p.H = a->heavy;
+        p.RW = (use == 2 && seg_narrow_ok(p.K)) ? 8 : VB_ROW_DOUBLES;
         if (use && (!p.RP || !p.H)) { vb_set_error("rpad / heavy workspace is NULL (see vb_bmm_ws_sizes)"); return VB_E_ARG; }
     }
     if (p.id_rows != 1 && p.id_rows != m->C) { vb_set_error("id_prior_rows must be 1 or n_cell"); return VB_E_ARG; }
@@ -979,17 +990,18 @@ static int ws_sizes(const vb_counts* m, int K, int G, int B, int T_is_V, vb_ws_s
     const int rc = want_gather(m, K, G != 0 && !T_is_V, &use);
     if (rc) return rc;
     p.tiled = use;
+    p.RW = (use == 2 && seg_narrow_ok(K)) ? 8 : VB_ROW_DOUBLES;
     part_layout(m, p);
     const int64_t T = T_is_V ? m->V : 1;
-    const int64_t Kw = use ? VB_ROW_DOUBLES : K;
+    const int64_t Kw = use ? p.RW : K;
     out->S = (int64_t)B * m->V * K;
     out->W = (int64_t)B * m->V * Kw * 2;
-    out->rpad = use ? (int64_t)B * m->C * VB_ROW_DOUBLES : 0;
+    out->rpad = use ? (int64_t)B * m->C * p.RW : 0;
     if (use == 3) {   // fixed-point copies (4 bytes per entry) behind the FP64 tables
         out->W += (int64_t)B * m->V * VB_ROW_DOUBLES;
         out->rpad += (int64_t)B * m->C * (VB_ROW_DOUBLES / 2);
     }
-    out->heavy = use ? (int64_t)B * (m->C > 2 * m->V ? m->C : 2 * m->V) * VB_ROW_DOUBLES : 0;
+    out->heavy = use ? (int64_t)B * (m->C > 2 * m->V ? m->C : 2 * m->V) * p.RW : 0;
     out->loglik = (int64_t)B * m->C * K;
     out->ab = (int64_t)B * T * 2 * (G ? G : 1) + (use == 3 ? B : 0);
     out->part = (int64_t)B * p.part_stride;
@@ -1064,7 +1076,7 @@ static int run_loop(const vb_counts* m, const EmP& p, int poll_every, cudaStream
     }
     VB_CUDA(cudaMemsetAsync(p.ctrl, 0, n_ctrl * sizeof(int32_t), st));
     if (p.tiled) {   // the SNP pass gathers ID_prob from its 128-byte-row copy
-        int rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.B, p.RP, st);
+        int rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.RW, p.B, p.RP, st);
         if (!rc && p.tiled == 3) rc = vb_seg_quantise_rows(m, p, st);
         if (rc) return rc;
     }
@@ -1110,7 +1122,7 @@ extern "C" int vb_vireo_step(const vb_counts* m, const vb_vireo_args* a, int pha
     VB_CUDA(cudaSetDevice(m->device));
     p.ctrl = nullptr;                       // single phases never consult the loop state
     if (p.tiled && (phases & VB_PH_SNP)) {
-        rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.B, p.RP, (cudaStream_t)stream);
+        rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.RW, p.B, p.RP, (cudaStream_t)stream);
         if (!rc && p.tiled == 3) rc = vb_seg_quantise_rows(m, p, (cudaStream_t)stream);
         if (rc) return rc;
     }
@@ -1132,7 +1144,7 @@ extern "C" int vb_bmm_step(const vb_counts* m, const vb_bmm_args* a, int phases,
     VB_CUDA(cudaSetDevice(m->device));
     p.ctrl = nullptr;
     if (p.tiled && (phases & VB_PH_SNP)) {
-        rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.B, p.RP, (cudaStream_t)stream);
+        rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.RW, p.B, p.RP, (cudaStream_t)stream);
         if (rc) return rc;
     }
     return bmm_iteration(m, p, phases, false, (cudaStream_t)stream);

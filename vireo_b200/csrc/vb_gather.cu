@@ -345,16 +345,16 @@ k_heavy(const GatherView gv, const double* __restrict__ table, int64_t table_str
     }
 }
 
-// replicate [n_row, K] into the 128-byte rows of a gather table: column c holds source column c % KT
+// replicate [n_row, K] into the rows (RW doubles each) of a gather table: column c holds source column c % KT
 __global__ void __launch_bounds__(VB_THREADS)
-k_pad_rows(const double* __restrict__ src, int64_t n_row, int K, int KT, double* __restrict__ dst) {
+k_pad_rows(const double* __restrict__ src, int64_t n_row, int K, int KT, int RW, double* __restrict__ dst) {
     const int b = blockIdx.y;
     const double* __restrict__ S = src + (size_t)b * n_row * K;
-    double* __restrict__ D = dst + (size_t)b * n_row * VB_ROW_DOUBLES;
-    const int64_t n = n_row * VB_ROW_DOUBLES;
+    double* __restrict__ D = dst + (size_t)b * n_row * RW;
+    const int64_t n = n_row * RW;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = e / VB_ROW_DOUBLES;
-        const int k = (int)(e % VB_ROW_DOUBLES) % KT;
+        const int64_t r = e / RW;
+        const int k = (int)(e % RW) % KT;
         D[e] = k < K ? S[r * K + k] : 0.0;
     }
 }
@@ -741,12 +741,12 @@ int vb_gather_launch(const vb_counts* m, const EmP& p, int ori, int mode, int th
     return VB_OK;
 }
 
-int vb_pad_rows_launch(const vb_counts* m, const double* src, int64_t n_row, int K, int KT, int B, double* dst,
+int vb_pad_rows_launch(const vb_counts* m, const double* src, int64_t n_row, int K, int KT, int RW, int B, double* dst,
                        cudaStream_t st) {
-    int64_t nb = (n_row * VB_ROW_DOUBLES + VB_THREADS - 1) / VB_THREADS;
+    int64_t nb = (n_row * RW + VB_THREADS - 1) / VB_THREADS;
     if (nb > (int64_t)m->sm_count * 8) nb = (int64_t)m->sm_count * 8;
     if (nb < 1) nb = 1;
-    VB_LAUNCH(7, st, k_pad_rows<<<dim3((unsigned)nb, B), VB_THREADS, 0, st>>>(src, n_row, K, KT, dst));
+    VB_LAUNCH(7, st, k_pad_rows<<<dim3((unsigned)nb, B), VB_THREADS, 0, st>>>(src, n_row, K, KT, RW, dst));
     VB_CUDA(cudaGetLastError());
     return VB_OK;
 }

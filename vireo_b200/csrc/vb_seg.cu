@@ -233,7 +233,7 @@ static int env_int(const char* name, int dflt) {
 // Look-ahead fill needs the windows w and w+1 resident while w+2 loads: nb >= 3.
 static void seg_window(int prec, int* win_rows, int* nb, int* look) {
     if (prec == 0) { *win_rows = env_int("VIREO_B200_SEG_WR64", 512); *nb = env_int("VIREO_B200_SEG_NB64", 3); }
-    else { *win_rows = env_int("VIREO_B200_SEG_WR32", 1024); *nb = env_int("VIREO_B200_SEG_NB32", 3); }
+    else { *win_rows = env_int("VIREO_B200_SEG_WR32", 1024); *nb = env_int("VIREO_B200_SEG_NB32", 3); }     // 64-byte rows
     *look = env_int("VIREO_B200_SEG_LOOK", 1) ? 1 : 0;
     if (*win_rows < 32) *win_rows = 32;
     if (*win_rows > VB_SEG_MAX_WIN_ROWS / 2) *win_rows = VB_SEG_MAX_WIN_ROWS / 2;     // 11-bit row offsets span two windows
@@ -247,7 +247,7 @@ static void seg_window(int prec, int* win_rows, int* nb, int* look) {
 
 static int seg_depth(int prec) {
     const int d = env_int(prec == 0 ? "VIREO_B200_SEG_DEPTH64" : "VIREO_B200_SEG_DEPTH32", prec == 0 ? VB_SEG_DEPTH64 : VB_SEG_DEPTH32);
-    return d >= 8 ? 8 : 4;
+    return (d >= 8 && prec != 2) ? 8 : 4;
 }
 
 template <int ORI>
@@ -382,8 +382,8 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
     VB_CUDA(cudaMalloc(&g.rec, n_rec * sizeof(uint16_t)));
     VB_CUDA(cudaMemsetAsync(g.rec, 0, n_rec * sizeof(uint16_t), st));
     if (O) {
-        if (m->wide) k_sg_fill<ORI, true><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, win_rows, n_win, prec == 1 ? 4 : 0, step_off, cnt_ow, take, g.rec, g.hptr, g.hrow, g.hcnt);
-        else k_sg_fill<ORI, false><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, win_rows, n_win, prec == 1 ? 4 : 0, step_off, cnt_ow, take, g.rec, g.hptr, g.hrow, g.hcnt);
+        if (m->wide) k_sg_fill<ORI, true><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, win_rows, n_win, prec != 0 ? 4 : 0, step_off, cnt_ow, take, g.rec, g.hptr, g.hrow, g.hcnt);
+        else k_sg_fill<ORI, false><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, win_rows, n_win, prec != 0 ? 4 : 0, step_off, cnt_ow, take, g.rec, g.hptr, g.hrow, g.hcnt);
         VB_CUDA(cudaGetLastError());
     }
     VB_CUDA(cudaStreamSynchronize(st));
@@ -402,7 +402,7 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
 }
 
 int vb_seg_build(vb_counts* m, int prec, cudaStream_t st) {
-    if (prec < 0 || prec > 1) { vb_set_error("bad table precision"); return VB_E_ARG; }
+    if (prec < 0 || prec > 2) { vb_set_error("bad table kind"); return VB_E_ARG; }
     if (m->sA[prec].built && m->sB[prec].built) return VB_OK;
     if (m->seg_failed[prec]) return VB_E_UNSUPPORTED;
     int rc = seg_build_one<0>(m, m->sA[prec], prec, st);
@@ -417,7 +417,7 @@ int vb_seg_build(vb_counts* m, int prec, cudaStream_t st) {
 }
 
 void vb_seg_free(vb_counts* m) {
-    for (int i = 0; i < 2; ++i) { seg_set_free(m->sA[i]); seg_set_free(m->sB[i]); }
+    for (int i = 0; i < 3; ++i) { seg_set_free(m->sA[i]); seg_set_free(m->sB[i]); }
 }
 
 void vb_seg_geometry(const SegSet& g, int* grid, int* nwarps) {
@@ -431,21 +431,21 @@ void vb_seg_geometry(const SegSet& g, int* grid, int* nwarps) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(VB_THREADS)
 k_seg_heavy(int64_t n_owner, const int64_t* __restrict__ hptr, const int32_t* __restrict__ hrow, const uint32_t* __restrict__ hcnt,
-            const double* __restrict__ table, int64_t table_stride, double* __restrict__ out, int64_t out_stride,
+            const double* __restrict__ table, int64_t table_stride, int RW, double* __restrict__ out, int64_t out_stride,
             const int* __restrict__ ctrl) {
     const int b = blockIdx.y;
     if (ctrl && ctrl[b * VB_CTRL_N]) return;
     const double* __restrict__ T = table + (size_t)b * table_stride;
     double* __restrict__ O = out + (size_t)b * out_stride;
-    const int lane = threadIdx.x & 31, kl = lane & 15, sub = lane >> 4;
+    const int lane = threadIdx.x & 31, kl = lane % RW, sub = lane / RW, nsub = 32 / RW;    // RW = 16 or 8
     const int64_t nw = (int64_t)gridDim.x * VB_WARPS;
     for (int64_t o = (int64_t)blockIdx.x * VB_WARPS + (threadIdx.x >> 5); o < n_owner; o += nw) {
         const int64_t p0 = hptr[o], p1 = hptr[o + 1];
         double acc = 0.0;
-        for (int64_t q = p0 + sub; q < p1; q += 2)
-            acc = fma((double)hcnt[q], T[(size_t)hrow[q] * VB_ROW_DOUBLES + kl], acc);
-        acc += __shfl_xor_sync(VB_FULL, acc, 16);
-        if (sub == 0) O[(size_t)o * VB_ROW_DOUBLES + kl] = acc;
+        for (int64_t q = p0 + sub; q < p1; q += nsub)
+            acc = fma((double)hcnt[q], T[(size_t)hrow[q] * RW + kl], acc);
+        for (int off = RW; off < 32; off <<= 1) acc += __shfl_xor_sync(VB_FULL, acc, off);
+        if (sub == 0) O[(size_t)o * RW + kl] = acc;
     }
 }
 
@@ -481,6 +481,7 @@ struct SegArgs {
 template <int PREC> struct SegCfg;
 template <> struct SegCfg<0> { static constexpr int LPO = 4, NC = 4, ROWB = 128; };
 template <> struct SegCfg<1> { static constexpr int LPO = 4, NC = 4, ROWB = 64; };
+template <> struct SegCfg<2> { static constexpr int LPO = 4, NC = 2, ROWB = 64; };     // FP64, 8 columns
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -492,6 +493,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // FP64 tables: 4 lanes x 4 columns, two 16-byte loads per lane.
 struct SegScratch64 { double v[2][4]; };     // landing registers of the FP64 loads, two sets in flight
 struct SegScratch32 {};
+struct SegScratchN { double v[2][2]; };         // narrow FP64 rows: one 16-byte load per lane and record
 
 template <bool HI, bool WRAP>
 __device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes, double (&a)[4],
@@ -523,6 +525,26 @@ __device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, uint32_t wra
     a[2] = fma(d, v[2], a[2]);
     a[3] = fma(d, v[3], a[3]);
 }
+// FP64 tables with 8 columns (n_donor <= 8): rows of 64 bytes, 4 lanes x 2 columns, one 16-byte load per lane.
+template <bool HI, bool WRAP>
+__device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes, double (&a)[2],
+                                         double (&v)[2]) {
+    const uint32_t c = HI ? (w & 0x001f0000u) : (w & 0x1fu);
+    uint32_t t;
+    asm("and.b32 %0, %1, %2;" : "=r"(t) : "r"(w), "r"(HI ? 0xffe00000u : 0xffe0u));
+    uint32_t off = HI ? __umulhi(t, 1u << 17) : t * 2u;    // row offset * 64 bytes
+    if (WRAP && off >= wrap_at) off -= ring_bytes;
+    const uint32_t addr = base + off;
+    const double d = __hiloint2double(0x43300000, (int)c) - 4503599627370496.0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p ld.shared.v2.f64 {%0, %1}, [%3];\n\t}"
+        : "+d"(v[0]), "+d"(v[1])
+        : "r"(c), "r"(addr));
+    a[0] = fma(d, v[0], a[0]);
+    a[1] = fma(d, v[1], a[1]);
+}
 // Fixed point: exact integer accumulation of count * value.  The upper record of a word is used in place
 // (count << 16, row offset << 16): the accumulators of odd slots carry a factor 2^16 that the epilogue removes
 // (safe while the reads of one owner stay below 2^16, checked when the format is built).
@@ -548,6 +570,12 @@ __device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, uint32_t wra
 template <bool WRAP>
 __device__ __forceinline__ void seg_super_step(const uint2& u, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes, double (&acc)[4][4],
                                                SegScratch64& sc) {
+    seg_step<false, WRAP>(u.x, base, wrap_at, ring_bytes, acc[0], sc.v[0]); seg_step<true, WRAP>(u.x, base, wrap_at, ring_bytes, acc[1], sc.v[1]);
+    seg_step<false, WRAP>(u.y, base, wrap_at, ring_bytes, acc[2], sc.v[0]); seg_step<true, WRAP>(u.y, base, wrap_at, ring_bytes, acc[3], sc.v[1]);
+}
+template <bool WRAP>
+__device__ __forceinline__ void seg_super_step(const uint2& u, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes, double (&acc)[4][2],
+                                               SegScratchN& sc) {
     seg_step<false, WRAP>(u.x, base, wrap_at, ring_bytes, acc[0], sc.v[0]); seg_step<true, WRAP>(u.x, base, wrap_at, ring_bytes, acc[1], sc.v[1]);
     seg_step<false, WRAP>(u.y, base, wrap_at, ring_bytes, acc[2], sc.v[0]); seg_step<true, WRAP>(u.y, base, wrap_at, ring_bytes, acc[3], sc.v[1]);
 }
@@ -592,7 +620,7 @@ __global__ void __launch_bounds__((VB_SEG_MAX_WARPS + 1) * 32, 1)
 k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     using Cfg = SegCfg<PREC>;
     constexpr int LPO = Cfg::LPO, M = Cfg::LPO, NC = Cfg::NC, ROWB = Cfg::ROWB;
-    typedef typename std::conditional<PREC == 0, double, unsigned long long>::type acc_t;
+    typedef typename std::conditional<PREC == 1, unsigned long long, double>::type acc_t;
     typedef uint2 chunk_t;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int b = blockIdx.y;
@@ -657,10 +685,14 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     } else if (task >= 0) {
         // ---------------- consumer warp: 32 owner slots, LPO lanes per slot
         const unsigned char* sp = reinterpret_cast<const unsigned char*>(sv.rec) + (size_t)sv.task_off[task] * (VB_SEG_OWNERS * 2) + g * (M * 2);
-        typename std::conditional<PREC == 0, SegScratch64, SegScratch32>::type sc;
+        typename std::conditional<PREC == 0, SegScratch64, typename std::conditional<PREC == 1, SegScratch32, SegScratchN>::type>::type sc;
         if constexpr (PREC == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) sc.v[i >> 2][i & 3] = 0.0;
+        }
+        if constexpr (PREC == 2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sc.v[i >> 1][i & 1] = 0.0;
         }
         chunk_t q[DEPTH];
 #pragma unroll
@@ -703,9 +735,11 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     // columns of this lane: [col0, col0 + 1] and [col0 + col2, col0 + col2 + 1]
     //   fixed point: four consecutive columns;  FP64: one granule in each half of the row, the first from the half
     //   this lane group reads first
-    const int col0 = PREC == 0 ? 2 * sub + 8 * (g & 1) : 4 * sub;
+    //   narrow FP64: two consecutive columns of 8
+    const int col0 = PREC == 0 ? 2 * sub + 8 * (g & 1) : (PREC == 1 ? 4 * sub : 2 * sub);
     const int col2 = PREC == 0 ? ((g & 1) ? -8 : 8) : 2;
-    const double unq = PREC == 0 ? 1.0 : (sa.mode == GM_SNP ? 1.0 / 4294967295.0 : -1.0 / p.qscale[b]);
+    const int RW = PREC == 2 ? 8 : VB_ROW_DOUBLES;
+    const double unq = PREC != 1 ? 1.0 : (sa.mode == GM_SNP ? 1.0 / 4294967295.0 : -1.0 / p.qscale[b]);
     const double unq_hi = unq / 65536.0;     // odd slots accumulate count << 16 (exact power of two in either precision)
 
     // the streaming task first, then a share of the tasks without records (accumulators are zero for those)
@@ -734,7 +768,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
                 primary[c] = col < KT && valid[c];
             }
             if (sa.has_heavy && owner >= 0) {
-                const double* __restrict__ H = p.H + ((size_t)b * sv.n_owner + owner) * VB_ROW_DOUBLES + col0;
+                const double* __restrict__ H = p.H + ((size_t)b * sv.n_owner + owner) * RW + col0;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) v[c] += H[c < 2 ? c : col2 + c - 2];
             }
@@ -765,12 +799,12 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
                     for (int c = 0; c < NC; ++c) pr[c] = pr[c] / z;
                     if (owner >= 0) {
                         // 128-byte-row copy (columns replicated 16/KT times) for the SNP pass
-                        double* __restrict__ RP = p.RP + ((size_t)b * p.C + j) * VB_ROW_DOUBLES + col0;
+                        double* __restrict__ RP = p.RP + ((size_t)b * p.C + j) * RW + col0;
                         *reinterpret_cast<double2*>(RP) = make_double2(pr[0], pr[1]);
-                        *reinterpret_cast<double2*>(RP + col2) = make_double2(pr[2], pr[3]);
+                        if constexpr (NC == 4) *reinterpret_cast<double2*>(RP + col2) = make_double2(pr[NC - 2], pr[NC - 1]);
                         if constexpr (PREC == 1) {
                             uint32_t* __restrict__ RQ = p.RPq + ((size_t)b * p.C + j) * VB_ROW_DOUBLES + col0;
-                            *reinterpret_cast<uint4*>(RQ) = make_uint4(quant_unit(pr[0]), quant_unit(pr[1]), quant_unit(pr[2]), quant_unit(pr[3]));
+                            *reinterpret_cast<uint4*>(RQ) = make_uint4(quant_unit(pr[0]), quant_unit(pr[1]), quant_unit(pr[NC - 2]), quant_unit(pr[NC - 1]));
                         }
                     }
                 } else {
@@ -884,13 +918,14 @@ static bool g_seg_attr_set = false;
 
 // ori 0: cell pass (table = p.Wt / p.Wq), ori 1: SNP pass (table = p.RP / p.RPq)
 int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, cudaStream_t st) {
-    const int prec = p.tiled == 3 ? 1 : 0;
+    const int prec = p.tiled == 3 ? 1 : (p.RW == 8 ? 2 : 0);
     const SegSet& g = ori ? m->sB[prec] : m->sA[prec];
     if (!g.built) { vb_set_error("segment format was not built"); return VB_E_ARG; }
     if (!g_seg_attr_set) {
         VB_CUDA(cudaFuncSetAttribute(k_seg<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         VB_CUDA(cudaFuncSetAttribute(k_seg<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         VB_CUDA(cudaFuncSetAttribute(k_seg<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VB_CUDA(cudaFuncSetAttribute(k_seg<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         VB_CUDA(cudaFuncSetAttribute(k_seg<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         g_seg_attr_set = true;
     }
@@ -902,7 +937,7 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
     memset(&sa, 0, sizeof(sa));
     sa.mode = mode; sa.theta_mode = theta_mode; sa.nb = nb;
     const double* tab64 = ori ? p.RP : p.Wt;
-    if (prec == 0) { sa.table = reinterpret_cast<const unsigned char*>(tab64); sa.table_stride = g.n_gather * 128; }
+    if (prec != 1) { sa.table = reinterpret_cast<const unsigned char*>(tab64); sa.table_stride = g.n_gather * (prec == 0 ? 128 : 64); }
     else { sa.table = reinterpret_cast<const unsigned char*>(ori ? p.RPq : p.Wq); sa.table_stride = g.n_gather * 64; }
     sa.has_heavy = g.n_heavy > 0;
     static const int wait_hint = env_int("VIREO_B200_SEG_WAIT_NS", 0);
@@ -915,13 +950,14 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
         if (hb > (int64_t)m->sm_count * 8) hb = (int64_t)m->sm_count * 8;
         if (hb < 1) hb = 1;
         VB_LAUNCH(cls, st, k_seg_heavy<<<dim3((unsigned)hb, p.B), VB_THREADS, 0, st>>>(
-            g.n_owner, g.hptr, g.hrow, g.hcnt, tab64, g.n_gather * VB_ROW_DOUBLES, p.H, g.n_owner * VB_ROW_DOUBLES, p.ctrl));
+            g.n_owner, g.hptr, g.hrow, g.hcnt, tab64, g.n_gather * p.RW, p.RW, p.H, g.n_owner * p.RW, p.ctrl));
         VB_CUDA(cudaGetLastError());
     }
     const dim3 grid(grid_x, p.B);
     const int threads = (sa.nwarps + 1) * 32;
     VB_LAUNCH(cls, st, {
-        if (prec == 0 && g.depth == 4) k_seg<0, 4><<<grid, threads, smem, st>>>(sv, p, sa);
+        if (prec == 2) k_seg<2, 4><<<grid, threads, smem, st>>>(sv, p, sa);
+        else if (prec == 0 && g.depth == 4) k_seg<0, 4><<<grid, threads, smem, st>>>(sv, p, sa);
         else if (prec == 0) k_seg<0, 8><<<grid, threads, smem, st>>>(sv, p, sa);
         else if (g.depth == 4) k_seg<1, 4><<<grid, threads, smem, st>>>(sv, p, sa);
         else k_seg<1, 8><<<grid, threads, smem, st>>>(sv, p, sa);

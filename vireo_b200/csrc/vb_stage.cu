@@ -195,18 +195,24 @@ extern "C" int64_t vb_counts_info(const vb_counts* m, int what) {
         case 16: return m->gA.n_light;
         // window-segment formats: 20 + 10 * precision + {0 built, 1 / 2 super-steps of the cell / SNP pass,
         // 3 / 4 largest reads of one owner's stream (cell / SNP pass), 5 / 6 grid.x, 7 bytes, 8 residual pairs, 9 stream pairs}
-        case 20: case 30: { const int q = what >= 30; return m->sA[q].built && m->sB[q].built; }
-        case 21: case 31: return m->sA[what >= 30].n_step;
-        case 22: case 32: return m->sB[what >= 30].n_step;
-        case 23: case 33: return m->sA[what >= 30].max_reads;
-        case 24: case 34: return m->sB[what >= 30].max_reads;
-        case 25: case 35: return m->sA[what >= 30].grid;
-        case 26: case 36: return m->sB[what >= 30].grid;
-        case 27: case 37: return m->sA[what >= 30].bytes + m->sB[what >= 30].bytes;
-        case 28: case 38: return m->sA[what >= 30].n_heavy;
-        case 29: case 39: return m->sA[what >= 30].n_light;
-        default: return -1;
+        default: break;
     }
+    if (what >= 20 && what < 50) {
+        const int q = (what - 20) / 10;          // 0 FP64 16 columns, 1 fixed point, 2 FP64 8 columns
+        switch ((what - 20) % 10) {
+            case 0: return m->sA[q].built && m->sB[q].built;
+            case 1: return m->sA[q].n_step;
+            case 2: return m->sB[q].n_step;
+            case 3: return m->sA[q].max_reads;
+            case 4: return m->sB[q].max_reads;
+            case 5: return m->sA[q].grid;
+            case 6: return m->sB[q].grid;
+            case 7: return m->sA[q].bytes + m->sB[q].bytes;
+            case 8: return m->sA[q].n_heavy;
+            case 9: return m->sA[q].n_light;
+        }
+    }
+    return -1;
 }
 
 extern "C" int vb_counts_create(int device, int64_t n_cell, int64_t n_var,
