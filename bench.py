@@ -416,6 +416,8 @@ def run_b200(args):
                     "identical_argmax_donor": same_argmax},
             }
             del batch32
+        except Exception as exc:                      # the opt-in leg must never take the headline down with it
+            fixed32 = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
         finally:
             _lib.set_path("auto")
     peaks = {}

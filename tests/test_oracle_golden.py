@@ -218,3 +218,25 @@ def test_synth_generator_is_deterministic():
     # pattern(AD) is a subset of pattern(DP), AD <= DP, no explicit zeros
     assert ((d1 - a1).data >= 0).all() and (a1.data > 0).all() and (d1.data > 0).all()
     assert (a1 > d1).nnz == 0 and a1.nnz <= d1.nnz
+
+
+def test_host_normalize_matches_numpy_bit_for_bit():
+    """vireo_b200.normalize takes a shortcut on a short last axis (the genotype axis); the inits it produces must
+    be the very arrays the reference's normalize (vireo_base.py:44-56) produces from the same random draws."""
+    from vireo_b200.vireo_base import normalize
+    rng = np.random.RandomState(0)
+    for shape in [(7, 3), (50, 16, 3), (9, 16), (4, 2), (3, 1), (6, 5), (5, 4, 4)]:
+        X = rng.rand(*shape)
+        assert np.array_equal(normalize(X), X / np.sum(X, axis=-1, keepdims=True)), shape
+    X = rng.rand(6, 5, 3)
+    assert np.array_equal(normalize(X, axis=1), X / np.sum(X, axis=1, keepdims=True))
+    import vireo_b200 as vb
+    np.random.seed(3)
+    m = vb.Vireo(n_cell=11, n_var=13, n_donor=4)
+    np.random.seed(3)
+    idp = np.random.rand(11, 4)
+    gtp = np.random.rand(13, 4, 3)
+    assert np.array_equal(m.ID_prob, idp / idp.sum(1, keepdims=True))
+    assert np.array_equal(m.GT_prob, gtp / gtp.sum(2, keepdims=True))
+    assert np.array_equal(m.ID_prior, np.ones((11, 4)) / np.sum(np.ones((11, 4)), axis=-1, keepdims=True))
+    assert np.array_equal(m.GT_prior, np.ones((13, 4, 3)) / np.sum(np.ones((13, 4, 3)), axis=-1, keepdims=True))
