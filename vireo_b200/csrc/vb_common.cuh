@@ -84,8 +84,8 @@ struct GatherView {
 //   window are padded with null records.  Record (16 bits):
 //       bits 15..5  gather row - w * win_rows        bits 4..0  count (0 = null)
 //   Pairs with count > 31 and all pairs of very short owners go to a residual CSR.
-//   The kernel binds LPO lanes to one owner slot (8 lanes x 2 FP64 columns, or 4 lanes x 4 fixed-point
-//   columns), so one warp step serves 32/LPO owners and the 32 slots of a super-step take LPO steps.
+//   The kernel binds 4 lanes to one owner slot (4 columns per lane; 2 for the 8-column FP64 tables), so one warp
+//   step serves 8 owners and the 32 slots of a super-step take 4 steps.
 // ----------------------------------------------------------------------------------------------
 #define VB_SEG_OWNERS 32
 #define VB_SEG_MAX_WARPS 22               // consumer warps per CTA (+1 producer warp)

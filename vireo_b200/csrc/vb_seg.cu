@@ -10,10 +10,12 @@
 // What bounds such a pass on B200 is the shared-memory crossbar (128 B/clk/SM): every pair needs one
 // table row.  The lane-per-owner kernels of vb_gather.cu spend 1.5 crossbar wavefronts per 128-byte
 // row because a quarter warp is rarely full.  Here
-//   * LPO lanes share one owner: the 8 (FP64) or 4 (fixed point) lanes read one contiguous row with a
-//     single 16-byte load each, so a wavefront always carries whole rows and is never bank-conflicted;
-//   * a warp task holds 32 owners: 32/LPO of them are served per warp step, the accumulators of all
-//     32 stay in registers (static indexing: the slot index is the unrolled loop variable);
+//   * 4 lanes share one owner and read its table row with 16-byte loads (two per lane for a 128-byte
+//     FP64 row -- one from each 64-byte half, even lane groups starting in the lower half and odd groups
+//     in the upper half so that the two rows of a wavefront never meet in a bank; one per lane for the
+//     64-byte rows), so a wavefront always carries whole rows;
+//   * a warp task holds 32 owners: 8 of them are served per warp step, the accumulators of all 32
+//     stay in registers (static indexing: the slot index is the unrolled loop variable);
 //   * the table streams through NB window buffers; a producer warp refills a buffer when every
 //     consumer warp has released it (full/empty mbarriers), consumers wait per window, not per record;
 //   * the records of a task are stored per window as super-steps of 32 x 16 bits; a segment (the
@@ -21,10 +23,11 @@
 //     in the slots that lock-step would otherwise pad with null records (look-ahead fill: 59% -> 85%
 //     useful slots); segments are padded to groups of DEPTH super-steps so that the register queue
 //     that prefetches them DEPTH super-steps ahead needs no rotation;
-//   * PREC 1 keeps the table as unsigned 32-bit fixed point (rows of 64 bytes: half the crossbar and
-//     L2 traffic) and accumulates count * value exactly in 64-bit integers, so the result does not
-//     depend on the summation order; the quantisation error is bounded per owner by
-//     sum(count) * 2^-33 * range and reported by vb_counts_info.
+//   * PREC 0: FP64 tables of 16 columns (rows of 128 bytes);  PREC 2: FP64 tables of 8 columns for
+//     n_donor <= 8 (rows of 64 bytes);  PREC 1 (opt-in) keeps 16 columns as unsigned 32-bit fixed point
+//     (rows of 64 bytes: half the crossbar traffic) and accumulates count * value exactly in 64-bit
+//     integers, so the result does not depend on the summation order; the quantisation error is bounded
+//     per owner by sum(count) * 2^-33 * range and reported by vb_counts_info.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <stdlib.h>
