@@ -185,6 +185,7 @@ def clear_cache():
     for _, s in list(_CACHE.values()):
         s.close()
     _CACHE.clear()
+    _PRIORS.clear()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -297,6 +298,57 @@ def replay_convergence(elbo, last, max_iter, min_iter, eps, bmm, verbose):
 # Vireo batches
 # ---------------------------------------------------------------------------------------------
 
+_PRIORS = {}
+
+
+def _fp_array(a):
+    a = np.asarray(a)
+    flat = a.reshape(-1) if a.flags.c_contiguous else a.ravel()
+    step = max(1, flat.size // 2048)
+    return (a.shape, a.dtype.str, a.ctypes.data, float(flat[::step].sum()) if flat.size else 0.0,
+            float(flat[0]) if flat.size else 0.0, float(flat[-1]) if flat.size else 0.0)
+
+
+def _vireo_priors(m0, dev, C_, V, K, G, T):
+    """Device-side priors of a Vireo model: logs of the donor and genotype priors (both flavours, see
+    ``_log_prior_pair``) and the theta prior.  They are constants of the model like the count matrices, so they are
+    cached the same way (object identity plus a sampled fingerprint): repeated fits of one model upload its state only."""
+    arrs = (m0.ID_prior, m0.GT_prior, m0.theta_s1_prior, m0.theta_s2_prior)
+    key = tuple(id(a) for a in arrs) + (dev, C_, V, K, G, T)
+    fp = tuple(_fp_array(a) for a in arrs)
+    hit = _PRIORS.get(key)
+    if hit is not None and hit[0] == fp:
+        return hit[1]
+    out = {}
+    id_prior = np.asarray(m0.ID_prior, dtype=np.float64)
+    if id_prior.ndim == 1:
+        id_prior = id_prior[None, :]
+    id_prior = _compress_rows(id_prior)
+    if id_prior.shape[0] not in (1, C_) or id_prior.shape[1] != K:
+        raise ValueError("ID_prior shape %r does not broadcast to (%d, %d)" % (id_prior.shape, C_, K))
+    out["id_rows"] = id_prior.shape[0]
+    out["lidp"], out["lidp_kl"] = _log_prior_pair(id_prior, dev)
+    gt_prior = np.asarray(m0.GT_prior, dtype=np.float64)
+    flat = np.broadcast_to(gt_prior, (V, K, G)).reshape(V * K, G)
+    if V * K > 1 and (flat == flat[:1]).all():
+        # one genotype prior for every (SNP, donor) -- the default: logs of one row, replicated on the device
+        raw, norm = _log_prior_pair(flat[:1], dev)
+        out["lgtp"] = raw.view(1, G).expand(V * K, G).contiguous().view(-1)
+        out["lgtp_kl"] = norm.view(1, G).expand(V * K, G).contiguous().view(-1)
+    else:
+        out["lgtp"], out["lgtp_kl"] = _log_prior_pair(flat, dev)
+    s1p = np.asarray(m0.theta_s1_prior, dtype=np.float64).reshape(-1, G)
+    s2p = np.asarray(m0.theta_s2_prior, dtype=np.float64).reshape(-1, G)
+    if s1p.shape[0] not in (1, T):
+        raise ValueError("theta prior has %d rows, expected 1 or %d" % (s1p.shape[0], T))
+    out["thp_rows"] = s1p.shape[0]
+    out["s1p"], out["s2p"] = _dev(s1p, dev), _dev(s2p, dev)
+    if len(_PRIORS) >= 8:
+        _PRIORS.pop(next(iter(_PRIORS)))
+    _PRIORS[key] = (fp, out)
+    return out
+
+
 class VireoBatch:
     """Device state of B Vireo restarts that share shapes, flags and priors."""
 
@@ -330,29 +382,10 @@ class VireoBatch:
         self.beta_mu = stack("beta_mu", (T, G))
         self.beta_sum = stack("beta_sum", (T, G))
 
-        id_prior = np.asarray(m0.ID_prior, dtype=np.float64)
-        if id_prior.ndim == 1:
-            id_prior = id_prior[None, :]
-        id_prior = _compress_rows(id_prior)
-        if id_prior.shape[0] not in (1, C_) or id_prior.shape[1] != K:
-            raise ValueError("ID_prior shape %r does not broadcast to (%d, %d)" % (id_prior.shape, C_, K))
-        self.id_rows = id_prior.shape[0]
-        self.lidp, self.lidp_kl = _log_prior_pair(id_prior, dev)
-        gt_prior = np.asarray(m0.GT_prior, dtype=np.float64)
-        flat = np.broadcast_to(gt_prior, (V, K, G)).reshape(V * K, G)
-        if V * K > 1 and (flat == flat[:1]).all():
-            # one genotype prior for every (SNP, donor) -- the default: logs of one row, replicated on the device
-            raw, norm = _log_prior_pair(flat[:1], dev)
-            self.lgtp = raw.view(1, G).expand(V * K, G).contiguous().view(-1)
-            self.lgtp_kl = norm.view(1, G).expand(V * K, G).contiguous().view(-1)
-        else:
-            self.lgtp, self.lgtp_kl = _log_prior_pair(flat, dev)
-        s1p = np.asarray(m0.theta_s1_prior, dtype=np.float64).reshape(-1, G)
-        s2p = np.asarray(m0.theta_s2_prior, dtype=np.float64).reshape(-1, G)
-        if s1p.shape[0] not in (1, T):
-            raise ValueError("theta prior has %d rows, expected 1 or %d" % (s1p.shape[0], T))
-        self.thp_rows = s1p.shape[0]
-        self.s1p, self.s2p = _dev(s1p, dev), _dev(s2p, dev)
+        pri = _vireo_priors(m0, dev, C_, V, K, G, T)
+        self.id_rows, self.thp_rows = pri["id_rows"], pri["thp_rows"]
+        self.lidp, self.lidp_kl, self.lgtp, self.lgtp_kl = pri["lidp"], pri["lidp_kl"], pri["lgtp"], pri["lgtp_kl"]
+        self.s1p, self.s2p = pri["s1p"], pri["s2p"]
 
         ws = _lib.WsSizes()
         _lib.check(_lib.load().vb_vireo_ws_sizes(counts.handle, K, G, B, int(self.ase), C.byref(ws)))
