@@ -126,7 +126,20 @@ def fit_cell_sharded(model, AD, DP, max_iter=200, min_iter=5, epsilon_conv=1e-2,
             x.copy_(tot)
 
     PH = _lib
+    # ELBO terms of every iteration stay on the device ({LB_p, KL_ID} summed over shards and ranks, KL_GT, KL_theta);
+    # the host reads them back only when the reference's rule could stop the loop (it > min_iter), so the first
+    # min_iter + 1 iterations -- all of them in a fixed-length fit -- are enqueued without a single synchronisation
+    terms = t.zeros((max_iter, 4), dtype=t.float64, device="cuda:%d" % dev)
     elbo = np.zeros(max_iter)
+    known = 0                      # iterations whose ELBO is on the host already
+
+    def fetch(upto):
+        nonlocal known
+        if upto > known:
+            h = terms[known:upto].cpu().numpy()
+            elbo[known:upto] = h[:, 0] - h[:, 1] - h[:, 2] - h[:, 3]
+            known = upto
+
     it = 0
     for it in range(max_iter):
         for _, _, b in batches:
@@ -139,14 +152,16 @@ def fit_cell_sharded(model, AD, DP, max_iter=200, min_iter=5, epsilon_conv=1e-2,
             phases |= PH.PH_GT
         for _, _, b in batches:
             b.run_step(phases)
-        # scal = {ELBO, LB_p, KL_ID, KL_GT, KL_theta}: the first two terms are sums over cells
+        # scal = {ELBO, LB_p, KL_ID, KL_GT, KL_theta}: LB_p and KL_ID are sums over cells
         parts = [b.scal[1:3].clone() for _, _, b in batches]
         reduce_(parts)
-        tail = batches[0][2].scal[3:5]
-        vals = t.cat([parts[0], tail]).cpu().numpy()
-        elbo[it] = vals[0] - vals[1] - vals[2] - vals[3]
-        if converged(elbo, it, min_iter, max_iter, epsilon_conv, verbose):
-            break
+        terms[it, 0:2].copy_(parts[0])
+        terms[it, 2:4].copy_(batches[0][2].scal[3:5])
+        if it > min_iter:
+            fetch(it + 1)
+            if converged(elbo, it, min_iter, max_iter, epsilon_conv, verbose):
+                break
+    fetch(it + 1)
 
     # results: GT_prob and theta are replicated, ID_prob is gathered
     b0 = batches[0][2]
