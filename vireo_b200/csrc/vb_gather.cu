@@ -306,6 +306,7 @@ static int build_one(vb_counts* m, GatherSet& g, cudaStream_t st) {
 int vb_gather_build(vb_counts* m, cudaStream_t st) {
     if (m->gA.built && m->gB.built) return VB_OK;
     if (m->gather_failed) return VB_E_UNSUPPORTED;
+    VB_CUDA(cudaSetDevice(m->device));
     int rc = build_one<0>(m, m->gA, st);
     if (!rc) rc = build_one<1>(m, m->gB, st);
     if (rc) {
@@ -684,7 +685,7 @@ void vb_gather_geometry(const vb_counts* m, const GatherSet& g, int* grid, int* 
     *nwarps = g.max_warps > 0 ? g.max_warps : 1;
 }
 
-static bool g_attr_set = false;
+static bool g_attr_set[64] = {false};         // per device: function attributes belong to the context
 
 template <int NL>
 static int launch_nl(const GatherView& gv, const EmP& p, const GatherArgs& ga, dim3 grid, cudaStream_t st) {
@@ -705,11 +706,12 @@ int vb_gather_launch(const vb_counts* m, const EmP& p, int ori, int mode, int th
                      cudaStream_t st) {
     const GatherSet& g = ori ? m->gB : m->gA;
     if (!g.built) { vb_set_error("gather format was not built"); return VB_E_ARG; }
-    if (!g_attr_set) {
+    const int dev_slot = m->device >= 0 && m->device < 64 ? m->device : 0;
+    if (!g_attr_set[dev_slot]) {
         VB_CUDA(cudaFuncSetAttribute(k_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_G_SMEM));
         VB_CUDA(cudaFuncSetAttribute(k_gather<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_G_SMEM));
         VB_CUDA(cudaFuncSetAttribute(k_gather<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_G_SMEM));
-        g_attr_set = true;
+        g_attr_set[dev_slot] = true;
     }
     const GatherView gv = view_of_set(g);
     GatherArgs ga;

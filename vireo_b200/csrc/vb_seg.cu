@@ -408,6 +408,7 @@ int vb_seg_build(vb_counts* m, int prec, cudaStream_t st) {
     if (prec < 0 || prec > 2) { vb_set_error("bad table kind"); return VB_E_ARG; }
     if (m->sA[prec].built && m->sB[prec].built) return VB_OK;
     if (m->seg_failed[prec]) return VB_E_UNSUPPORTED;
+    VB_CUDA(cudaSetDevice(m->device));
     int rc = seg_build_one<0>(m, m->sA[prec], prec, st);
     if (!rc) rc = seg_build_one<1>(m, m->sB[prec], prec, st);
     if (rc) {
@@ -917,20 +918,21 @@ static size_t seg_smem(int prec, int nb, int win_rows) {
     return (size_t)nb * win_rows * (prec == 0 ? 128 : 64) + 16 * 8 + (size_t)(VB_SEG_MAX_WARPS + 1) * VB_SG_RED_DOUBLES * 8;
 }
 
-static bool g_seg_attr_set = false;
+static bool g_seg_attr_set[64] = {false};     // per device: function attributes belong to the context
 
 // ori 0: cell pass (table = p.Wt / p.Wq), ori 1: SNP pass (table = p.RP / p.RPq)
 int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, cudaStream_t st) {
     const int prec = p.tiled == 3 ? 1 : (p.RW == 8 ? 2 : 0);
     const SegSet& g = ori ? m->sB[prec] : m->sA[prec];
     if (!g.built) { vb_set_error("segment format was not built"); return VB_E_ARG; }
-    if (!g_seg_attr_set) {
+    const int dev_slot = m->device >= 0 && m->device < 64 ? m->device : 0;
+    if (!g_seg_attr_set[dev_slot]) {
         VB_CUDA(cudaFuncSetAttribute(k_seg<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         VB_CUDA(cudaFuncSetAttribute(k_seg<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         VB_CUDA(cudaFuncSetAttribute(k_seg<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         VB_CUDA(cudaFuncSetAttribute(k_seg<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         VB_CUDA(cudaFuncSetAttribute(k_seg<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        g_seg_attr_set = true;
+        g_seg_attr_set[dev_slot] = true;
     }
     const int nb = g.nb;
     const size_t smem = seg_smem(prec, nb, g.win_rows);
