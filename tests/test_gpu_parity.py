@@ -570,3 +570,33 @@ def test_cell_sharded_fit_matches_single_fit(vb, cellsnp, kernel_path):
         rel_close(b.beta_mu, a.beta_mu, _ptol(), "beta_mu")
         rel_close(b.beta_sum, a.beta_sum, _ptol(), "beta_sum")
         assert np.array_equal(a.ID_prob.argmax(1), b.ID_prob.argmax(1))
+
+
+def test_prior_cache_follows_the_model(vb, small):
+    """The device-side priors are cached per model (identity + fingerprint, like the staged matrices): a prior that is
+    replaced or edited in place between two fits must be picked up, and an untouched one must give identical results."""
+    AD, DP = small
+    K = 3
+    np.random.seed(21)
+    m = vb.Vireo(n_cell=AD.shape[1], n_var=AD.shape[0], n_donor=K)
+    start = (m.ID_prob.copy(), m.GT_prob.copy(), m.beta_mu.copy(), m.beta_sum.copy())
+
+    def refit(model):
+        model.ID_prob, model.GT_prob = start[0].copy(), start[1].copy()
+        model.beta_mu, model.beta_sum = start[2].copy(), start[3].copy()
+        model.ELBO_ = np.zeros(0)
+        model.fit(AD, DP, max_iter=10, min_iter=10, verbose=False)
+        return model.ELBO_.copy(), model.ID_prob.copy()
+
+    e0, r0 = refit(m)
+    e1, r1 = refit(m)                                   # cache hit: identical
+    assert np.array_equal(e0, e1) and np.array_equal(r0, r1)
+    skew = np.tile(np.array([[0.7, 0.2, 0.1]]), (AD.shape[1], 1))
+    m.ID_prior[...] = skew                              # edited in place: same object, new content
+    e2, r2 = refit(m)
+    fresh = vb.Vireo(n_cell=AD.shape[1], n_var=AD.shape[0], n_donor=K)
+    fresh.set_prior(ID_prior=skew.copy())
+    e3, r3 = refit(fresh)
+    assert not np.array_equal(e2, e0)
+    rel_close(e2, e3, 1e-12, "ELBO after an in-place prior edit")
+    rel_close(r2, r3, 1e-9, "ID_prob after an in-place prior edit")
