@@ -113,14 +113,24 @@ k_cell(const CountsView m, const EmP p, const int mode, const int k_off) {
 #pragma unroll
         for (int r = 0; r < KR; ++r) acc[r] = 0.0;
         const int64_t p0 = m.cell_ptr[j], p1 = m.cell_ptr[j + 1];
+        // the records of the next 32 nnz are requested before the current 32 are processed (one load latency per
+        // batch off the dependent chain index -> table row -> FMA)
+        int idx_n = 0;
+        uint32_t c_n = 0, d_n = 0;
+        if (p0 + lane < p1) {
+            idx_n = __ldg(m.cell_idx + p0 + lane);
+            c_n = __ldg(m.cell_cnt + p0 + lane);
+            if (WIDE) d_n = __ldg(m.cell_dp + p0 + lane);
+        }
         for (int64_t base = p0; base < p1; base += 32) {
-            const int64_t q = base + lane;
-            int idx = 0;
-            uint32_t c = 0, d = 0;
-            if (q < p1) {
-                idx = __ldg(m.cell_idx + q);
-                c = __ldg(m.cell_cnt + q);
-                if (WIDE) d = __ldg(m.cell_dp + q);
+            const int idx = idx_n;
+            const uint32_t c = c_n, d = d_n;
+            const int64_t qn = base + 32 + lane;
+            idx_n = 0; c_n = 0; d_n = 0;
+            if (qn < p1) {
+                idx_n = __ldg(m.cell_idx + qn);
+                c_n = __ldg(m.cell_cnt + qn);
+                if (WIDE) d_n = __ldg(m.cell_dp + qn);
             }
             const int n = (int)((p1 - base) < 32 ? (p1 - base) : 32);
 #pragma unroll 4
@@ -243,14 +253,22 @@ k_snp(const CountsView m, const EmP p, const int theta_mode) {
 #pragma unroll
         for (int r = 0; r < KR; ++r) a1[r] = a2[r] = 0.0;
         const int64_t p0 = m.snp_ptr[i], p1 = m.snp_ptr[i + 1];
+        int idx_n = 0;                 // next batch of records, requested one batch ahead (see k_cell)
+        uint32_t c_n = 0, d_n = 0;
+        if (p0 + lane < p1) {
+            idx_n = __ldg(m.snp_idx + p0 + lane);
+            c_n = __ldg(m.snp_cnt + p0 + lane);
+            if (WIDE) d_n = __ldg(m.snp_dp + p0 + lane);
+        }
         for (int64_t base = p0; base < p1; base += 32) {
-            const int64_t q = base + lane;
-            int idx = 0;
-            uint32_t c = 0, d = 0;
-            if (q < p1) {
-                idx = __ldg(m.snp_idx + q);
-                c = __ldg(m.snp_cnt + q);
-                if (WIDE) d = __ldg(m.snp_dp + q);
+            const int idx = idx_n;
+            const uint32_t c = c_n, d = d_n;
+            const int64_t qn = base + 32 + lane;
+            idx_n = 0; c_n = 0; d_n = 0;
+            if (qn < p1) {
+                idx_n = __ldg(m.snp_idx + qn);
+                c_n = __ldg(m.snp_cnt + qn);
+                if (WIDE) d_n = __ldg(m.snp_dp + qn);
             }
             const int n = (int)((p1 - base) < 32 ? (p1 - base) : 32);
 #pragma unroll 4
