@@ -353,6 +353,178 @@ k_snp(const CountsView m, const EmP p, const int theta_mode) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row kernels for few donors (K <= 8), one warp per row, one LANE per nnz: every lane gathers the whole K-wide table
+// row(s) of its own nnz and keeps K private accumulators, so 32 nnz are in flight per step instead of 32/KT -- the
+// passes of small matrices are chains of dependent L2 latencies, and this shortens the chain four- to eightfold.
+// The K accumulators are folded across the warp once per row (xor butterfly: every lane ends with the same bits).
+// ---------------------------------------------------------------------------------------------
+template <int KP>
+__device__ __forceinline__ void warp_fold(double (&a)[KP]) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int k = 0; k < KP; ++k) a[k] += __shfl_xor_sync(VB_FULL, a[k], off);
+}
+
+template <int KP, bool WIDE>
+__global__ void __launch_bounds__(VB_THREADS)
+k_cell_lane(const CountsView m, const EmP p, const int mode) {
+    const int b = blockIdx.y;
+    if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int K = p.K;
+    const double* __restrict__ Wt = p.Wt + (size_t)b * p.V * 2 * K;
+    double* __restrict__ R = p.R ? p.R + (size_t)b * p.C * K : nullptr;
+    double* __restrict__ LL = p.ll + (size_t)b * p.C * K;
+    double lbp = 0.0, klid = 0.0;
+    const int64_t nw = (int64_t)gridDim.x * VB_WARPS;
+    for (int64_t j = (int64_t)blockIdx.x * VB_WARPS + wib; j < p.C; j += nw) {
+        double acc[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[k] = 0.0;
+        const int64_t p1 = m.cell_ptr[j + 1];
+        for (int64_t q = m.cell_ptr[j] + lane; q < p1; q += 32) {
+            int av, bv;
+            decode<WIDE>(__ldg(m.cell_cnt + q), WIDE ? __ldg(m.cell_dp + q) : 0u, av, bv);
+            const double* __restrict__ row = Wt + (size_t)__ldg(m.cell_idx + q) * 2 * K;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                if (k < K) {
+                    if (bv) acc[k] = axpy_count(bv, __ldg(row + k), acc[k]);
+                    if (av) acc[k] = axpy_count(av, __ldg(row + K + k), acc[k]);
+                }
+            }
+        }
+        warp_fold<KP>(acc);
+        const size_t prow = (size_t)(p.id_rows == 1 ? 0 : j) * K;
+        double pr[KP];
+        if (mode == 0) {
+            double mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                pr[k] = k < K ? acc[k] + p.lidp[prow + k] : -INFINITY;
+                mx = fmax(mx, pr[k]);
+            }
+            double z = 0.0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                pr[k] = k < K ? exp(pr[k] - mx) : 0.0;
+                z += pr[k];
+            }
+#pragma unroll
+            for (int k = 0; k < KP; ++k) pr[k] = pr[k] / z;
+        } else {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) pr[k] = k < K ? R[(size_t)j * K + k] : 0.0;
+        }
+        // lane k owns column k of the outputs and of the ELBO partial sums
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            if (k == lane && k < K) {
+                const size_t e = (size_t)j * K + k;
+                LL[e] = acc[k];
+                if (mode == 0) R[e] = pr[k];
+                lbp += acc[k] * pr[k];
+                if (pr[k] > 0.0) klid += pr[k] * (log(pr[k]) - p.lidp_kl[prow + k]);
+            }
+        }
+    }
+    __shared__ double sh[VB_WARPS];
+    const double t0 = block_sum(lbp, sh);
+    const double t1 = block_sum(klid, sh);
+    if (threadIdx.x == 0) {
+        double* out = p.part + (size_t)b * p.part_stride + p.off_cell + 2 * blockIdx.x;
+        out[0] = t0;
+        out[1] = t1;
+    }
+}
+
+template <int KP, bool WIDE>
+__global__ void __launch_bounds__(VB_THREADS)
+k_snp_lane(const CountsView m, const EmP p, const int theta_mode) {
+    const int b = blockIdx.y;
+    if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
+    const bool do_theta = !p.bmm && vb_theta_on(p, b, theta_mode);
+    if (!p.bmm && !do_theta && !p.learn_gt && theta_mode == 2) return;   // nothing consumes S1/S2 this iteration
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int K = p.K, G = p.G;
+    const double* __restrict__ R = p.R + (size_t)b * p.C * K;
+    const double* __restrict__ GT = p.GT ? p.GT + (size_t)b * p.V * K * G : nullptr;
+    double* __restrict__ S1 = p.S1 + (size_t)b * p.V * K;
+    double* __restrict__ S2 = p.S2 + (size_t)b * p.V * K;
+    double t1[VB_MAX_GT], t2[VB_MAX_GT];
+#pragma unroll
+    for (int g = 0; g < VB_MAX_GT; ++g) t1[g] = t2[g] = 0.0;
+    const int64_t nw = (int64_t)gridDim.x * VB_WARPS;
+    for (int64_t i = (int64_t)blockIdx.x * VB_WARPS + wib; i < p.V; i += nw) {
+        double a1[KP], a2[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) a1[k] = a2[k] = 0.0;
+        const int64_t p1 = m.snp_ptr[i + 1];
+        for (int64_t q = m.snp_ptr[i] + lane; q < p1; q += 32) {
+            int av, bv;
+            decode<WIDE>(__ldg(m.snp_cnt + q), WIDE ? __ldg(m.snp_dp + q) : 0u, av, bv);
+            const double* __restrict__ row = R + (size_t)__ldg(m.snp_idx + q) * K;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                if (k < K) {
+                    const double w = __ldg(row + k);
+                    if (av) a1[k] = axpy_count(av, w, a1[k]);
+                    if (bv) a2[k] = axpy_count(bv, w, a2[k]);
+                }
+            }
+        }
+        warp_fold<KP>(a1);
+        warp_fold<KP>(a2);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            if (k == lane && k < K) {
+                const size_t e = (size_t)i * K + k;
+                S1[e] = a1[k];
+                S2[e] = a2[k];
+                if (do_theta) {
+#pragma unroll
+                    for (int g = 0; g < VB_MAX_GT; ++g)
+                        if (g < G) {
+                            const double gt = GT[e * G + g];
+                            t1[g] += a1[k] * gt;
+                            t2[g] += a2[k] * gt;
+                        }
+                }
+            }
+        }
+        if (do_theta && p.ase) {
+            // allele-specific mode: theta per SNP (vireo_model.py:177): the raw sums are parked in the ab rows
+            double* row = p.ab + ((size_t)b * p.T + i) * 2 * G;
+#pragma unroll
+            for (int g = 0; g < VB_MAX_GT; ++g)
+                if (g < G) {
+                    const double u1 = warp_sum(t1[g]), u2 = warp_sum(t2[g]);
+                    if (lane == 0) { row[g] = u1; row[G + g] = u2; }
+                    t1[g] = t2[g] = 0.0;
+                }
+        }
+    }
+    if (!do_theta || p.ase) return;
+    __shared__ double sh[VB_WARPS][2 * VB_MAX_GT];
+#pragma unroll
+    for (int g = 0; g < VB_MAX_GT; ++g) {
+        if (g < G) {
+            const double u1 = warp_sum(t1[g]), u2 = warp_sum(t2[g]);
+            if (lane == 0) { sh[wib][g] = u1; sh[wib][VB_MAX_GT + g] = u2; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * VB_MAX_GT) {
+        const int g = threadIdx.x % VB_MAX_GT;
+        double t = 0.0;
+        if (g < G)
+            for (int w = 0; w < VB_WARPS; ++w) t += sh[w][threadIdx.x];
+        p.part[(size_t)b * p.part_stride + p.off_theta + (size_t)blockIdx.x * 2 * VB_MAX_GT + threadIdx.x] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_theta (shared theta, T = 1): one CTA per restart
 // ---------------------------------------------------------------------------------------------
 struct ThetaOut { double A, B, kl; };
@@ -822,6 +994,15 @@ static bool tile_for(int K, int& KT, int& KR) {
         }                                                                         \
     } while (0)
 
+// lane-per-nnz row kernels serve K <= 8 when the rows are long enough to fill the lanes for a few steps (measured
+// at 10k x 5k x 4: SNP rows of ~200 nnz 28.7 -> 24.7 us, cell rows of ~100 nnz 25.9 -> 30.8 us);
+// VIREO_B200_ROWS_LANE=0 keeps the KT-lanes-per-nnz kernels, =2 forces the lane kernels
+static bool rows_lane_ok(int K, int64_t nnz, int64_t n_row) {
+    static const int mode = getenv("VIREO_B200_ROWS_LANE") ? atoi(getenv("VIREO_B200_ROWS_LANE")) : 1;
+    if (mode == 0 || K > 8) return false;
+    return mode == 2 || nnz >= 160 * (n_row > 0 ? n_row : 1);
+}
+
 static int launch_cell(const vb_counts* m, const EmP& p, int mode, cudaStream_t st) {
     if (p.tiled >= 2) return vb_seg_launch(m, p, 0, mode == 0 ? GM_CELL : GM_CELL_LL, 0, st);
     if (p.tiled) return vb_gather_launch(m, p, 0, mode == 0 ? GM_CELL : GM_CELL_LL, 0, nullptr, st);
@@ -829,6 +1010,14 @@ static int launch_cell(const vb_counts* m, const EmP& p, int mode, cudaStream_t 
     if (!tile_for(p.K, KT, KR)) { vb_set_error("n_donor=%d outside [1, %d]", p.K, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
     const CountsView v = view_of(m);
     const dim3 grid(m->grid_cell, p.B);
+    if (rows_lane_ok(p.K, m->N, m->C)) {
+        VB_LAUNCH(3, st, {
+            if (p.K <= 4) { if (m->wide) k_cell_lane<4, true><<<grid, VB_THREADS, 0, st>>>(v, p, mode); else k_cell_lane<4, false><<<grid, VB_THREADS, 0, st>>>(v, p, mode); }
+            else { if (m->wide) k_cell_lane<8, true><<<grid, VB_THREADS, 0, st>>>(v, p, mode); else k_cell_lane<8, false><<<grid, VB_THREADS, 0, st>>>(v, p, mode); }
+        });
+        VB_CUDA(cudaGetLastError());
+        return VB_OK;
+    }
     VB_LAUNCH(3, st, VB_DISPATCH_TILE(KT, KR, m->wide, k_cell<kt, kr, wd, true><<<grid, VB_THREADS, 0, st>>>(v, p, mode, 0)));
     VB_CUDA(cudaGetLastError());
     return VB_OK;
@@ -841,6 +1030,14 @@ static int launch_snp(const vb_counts* m, const EmP& p, int theta_mode, cudaStre
     if (!tile_for(p.K, KT, KR)) { vb_set_error("n_donor=%d outside [1, %d]", p.K, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
     const CountsView v = view_of(m);
     const dim3 grid(m->grid_snp, p.B);
+    if (rows_lane_ok(p.K, m->N, m->V)) {
+        VB_LAUNCH(0, st, {
+            if (p.K <= 4) { if (m->wide) k_snp_lane<4, true><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); else k_snp_lane<4, false><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); }
+            else { if (m->wide) k_snp_lane<8, true><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); else k_snp_lane<8, false><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); }
+        });
+        VB_CUDA(cudaGetLastError());
+        return VB_OK;
+    }
     VB_LAUNCH(0, st, VB_DISPATCH_TILE(KT, KR, m->wide, k_snp<kt, kr, wd><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode)));
     VB_CUDA(cudaGetLastError());
     return VB_OK;
