@@ -19,6 +19,8 @@
  *  - matrices are float64, C order; B = n_batch independent restarts are laid
  *    out with the restart index outermost.
  *  - a vb_counts handle is not thread-safe; use one per (process, GPU).
+ *  - every entry point runs on the device of the handle it is given and restores the calling thread's
+ *    current CUDA device before it returns.
  */
 #ifndef VIREO_B200_H
 #define VIREO_B200_H
@@ -74,14 +76,22 @@ int vb_counts_create(int device, int64_t n_cell, int64_t n_var,
                      const void* ad_indptr, const void* ad_indices, const void* ad_data, int64_t ad_nnz,
                      void* stream, vb_counts** out);
 void vb_counts_destroy(vb_counts* m);
+/* A second handle holding the columns (cells) [cell_begin, cell_end) of a staged pair, built on the device from
+ * the resident arrays (no host traffic): the cell shard one rank owns in a cell-sharded fit
+ * (vb_vireo_fit_sharded).  Equivalent to staging AD[:, cell_begin:cell_end], DP[:, cell_begin:cell_end]. */
+int vb_counts_slice(const vb_counts* m, int64_t cell_begin, int64_t cell_end, void* stream, vb_counts** out);
 /* shape / layout queries: what = 0 n_cell, 1 n_var, 2 nnz, 3 wide flag, 4 device, 5 bytes resident,
  * 6 grid.x of the cell pass (rows path), 7 grid.x of the SNP pass (rows path), 8 grid.x of the elementwise
- * (V*K) kernels, 9 gather-stream formats built, 10 / 11 stream records of the cell / SNP pass, 12 residual
- * (count >= 32) pairs, 13 bytes of the gather formats, 14 / 15 grid.x of the gather cell / SNP pass,
- * 16 pairs carried by the streams; window-segment formats: 20 + 10 * precision (0 FP64, 1 fixed point) +
- * {0 built, 1 / 2 super-steps of the cell / SNP pass, 3 / 4 largest reads of one row's stream (cell / SNP pass;
- * fixed-point error bound = reads * 2^-33 * table range), 5 / 6 grid.x, 7 bytes, 8 residual pairs, 9 stream pairs} */
+ * (V*K) kernels; window-segment formats: 20 + 10 * table kind (0 FP64 rows of 16 columns, 1 fixed point,
+ * 2 FP64 rows of 8 columns) + {0 built, 1 / 2 super-steps of the cell / SNP pass, 3 / 4 largest reads of one
+ * row's stream (cell / SNP pass; fixed-point error bound = reads * 2^-33 * table range), 5 / 6 grid.x, 7 bytes,
+ * 8 residual pairs, 9 stream pairs};
+ * 60: why the automatic selector last served this matrix with the row kernels: 0 it did not, 1 small matrix
+ *     (by design), 2 building the segment formats FAILED (vb_counts_note has the message; the row kernels are
+ *     several times slower on large matrices), 3 residual-dominated counts (by design), 4 n_donor > 16 */
 int64_t vb_counts_info(const vb_counts* m, int what);
+/* message of the failed format build behind vb_counts_info(m, 60) == 2 ("" otherwise) */
+const char* vb_counts_note(const vb_counts* m);
 
 /* sum over nnz(DP>0) of float32(min(log C(dp, ad), 700)), accumulated in float64.
  * Replaces np.sum(get_binom_coeff(AD, DP)) (vireoSNP/utils/vireo_base.py:7-22, vireo_model.py:313,
@@ -96,7 +106,7 @@ typedef struct vb_ws_sizes {
     int64_t ab;       /* doubles: [B, T, 2*G] digamma differences              */
     int64_t part;     /* doubles: block partial sums                           */
     int64_t scal;     /* doubles: [B, 8] ELBO terms                            */
-    int64_t ctrl;     /* int32:   [B, 4] {done, it, n_decrease, hit_max}       */
+    int64_t ctrl;     /* int32:   [B, 4] {done, it_next, last_it, n_decrease}  */
     int64_t rpad;     /* doubles: ID_prob in 128-byte rows [B, n_cell, 16] (gather path, else 0) */
     int64_t heavy;    /* doubles: residual sums [B, max(n_cell, 2 n_var), 16] (gather path, else 0) */
 } vb_ws_sizes;
@@ -129,9 +139,16 @@ typedef struct vb_vireo_args {
     double* elbo;                /* [B, max_iter] every computed ELBO (the reference returns ELBO[:it]) */
     /* gather-path workspace (may be NULL when vb_vireo_ws_sizes reports 0) */
     double *rpad, *heavy;
+    /* element counts of the workspaces as the caller allocated them (copy of what vb_vireo_ws_sizes returned):
+     * every entry point checks them against what the kernel family it is about to launch needs and fails with
+     * VB_E_ARG instead of writing out of bounds (the family can change between sizing and launching, e.g.
+     * through vb_set_path) */
+    vb_ws_sizes ws;
 } vb_vireo_args;
 
-int vb_vireo_ws_sizes(const vb_counts* m, int n_donor, int n_gt, int n_batch, int ase_mode, vb_ws_sizes* out);
+/* `stream`: formats a kernel family needs are built lazily on first use, on this stream */
+int vb_vireo_ws_sizes(const vb_counts* m, int n_donor, int n_gt, int n_batch, int ase_mode, void* stream,
+                      vb_ws_sizes* out);
 
 /* Priors enter the kernels as logs, in two flavours: log(prior) as the softmax adds it
  * (vireoSNP/utils/vireo_model.py:198,218; bmm_model.py:153) and the log of the row-normalised prior that
@@ -142,8 +159,9 @@ int vb_log_prior(const double* prior, int64_t n_row, int n_col, double* log_raw,
 /* Run the coordinate-ascent loop of Vireo._fit_VB (vireoSNP/utils/vireo_model.py:251-276) for a batch
  * of restarts entirely on the device: per iteration update_theta_size (:165-185), update_GT_prob
  * (:204-219), update_ID_prob (:187-201) and get_ELBO (:222-248), with the reference's convergence
- * rule evaluated on the device.  On return ctrl[b] = {done, it, ...}: `it` is the index of the last
- * executed iteration, so the reference's return value is elbo[b, 0:it].
+ * rule evaluated on the device.  On return ctrl[b] = {done, it_next, last_it, n_decrease}: `last_it` is the
+ * index of the last executed iteration, so the reference's return value is elbo[b, 0:last_it].
+ * Small matrices (launch-bound iterations) replay one captured CUDA graph per group of iterations.
  * The binomial constant (vireo_model.py:313) is NOT added here; see vb_binom_const. */
 int vb_vireo_fit(const vb_counts* m, const vb_vireo_args* a, void* stream);
 
@@ -170,9 +188,10 @@ typedef struct vb_bmm_args {
     int32_t* ctrl;
     double* elbo;                /* [B, max_iter]                                                     */
     double *rpad, *heavy;        /* gather-path workspace (may be NULL when vb_bmm_ws_sizes reports 0) */
+    vb_ws_sizes ws;              /* allocated element counts, checked like vb_vireo_args.ws */
 } vb_bmm_args;
 
-int vb_bmm_ws_sizes(const vb_counts* m, int n_donor, int n_batch, vb_ws_sizes* out);
+int vb_bmm_ws_sizes(const vb_counts* m, int n_donor, int n_batch, void* stream, vb_ws_sizes* out);
 
 /* BinomMixtureVB._fit_BV (vireoSNP/utils/bmm_model.py:178-201) for a batch of restarts:
  * update_theta_size (:133-144), get_E_logLik (:118-130), update_ID_prob (:147-154), get_ELBO (:157-175). */
@@ -182,16 +201,58 @@ int vb_bmm_step(const vb_counts* m, const vb_bmm_args* a, int phases, void* stre
 /* Doublet pass of predict_doublet (vireoSNP/utils/vireo_doublet.py:39-68): builds the K + K(K-1)/2
  * column tables from GT_prob [n_var,K,G] and theta (add_doublet_GT :105-136, add_doublet_theta
  * :85-102) on the device, runs the cell-major logLik pass and the softmax with the doublet prior.
+ * Large matrices run the K2 columns as chunks of 16 through the window-segment kernel (one pass of the record
+ * stream per chunk), small ones through the row kernels.
  *   loglik_out, prob_out: [n_cell, K2] with K2 = K + K(K-1)/2;  llr_out: [n_cell]
- *   W: workspace [n_var, 2, K2];  log_prior_both: [id_prior_rows, K2]. */
+ *   log_prior_both: [id_prior_rows, K2]
+ *   W, heavy, ab2: workspaces sized by vb_doublet_ws_sizes (elements, doubles); the call allocates nothing and
+ *   does not synchronise the stream. */
+typedef struct vb_doublet_ws { int64_t W, heavy, ab2; } vb_doublet_ws;
+int vb_doublet_ws_sizes(const vb_counts* m, int n_donor, int n_gt, int ase_mode, void* stream, vb_doublet_ws* out);
 int vb_vireo_doublet(const vb_counts* m, int n_donor, int n_gt, int ase_mode,
                      const double* gt_prob, const double* beta_mu, const double* beta_sum,
                      const double* log_prior_both, int id_prior_rows,
-                     double* W, double* loglik_out, double* prob_out, double* llr_out,
+                     double* W, double* heavy, double* ab2, const vb_doublet_ws* ws,
+                     double* loglik_out, double* prob_out, double* llr_out,
                      void* stream);
 
+/* ---- one fit over several GPUs: cells sharded over ranks ------------------------------------
+ * For the fits restart sharding cannot spread: the final fit of vireo_wrap (vireoSNP/utils/vireo_wrap.py:94)
+ * and the GT-given mode (one restart, :48-50).  Rank r holds the staged columns of its cells (vb_counts_slice)
+ * and their ID_prob rows; GT_prob and theta are replicated.  One EM iteration (vireo_model.py:257-264):
+ *     SNP pass over the local cells            S1_r | S2_r                        (:168-170, :207-209)
+ *     ONE all-reduce (sum) over the ranks      S1 | S2 | {LB_p, KL_ID} of the previous iteration
+ *     ELBO + convergence rule of the previous iteration (:248, :266-274) -- identical on every rank
+ *     theta sums, theta, GT update             identical on every rank            (:173-185, :211-219)
+ *     cell pass over the local cells           ID_prob_r, local LB_p and KL_ID    (:190-201, :236-237)
+ * i.e. the two cell-summed ELBO terms ride on the next iteration's exchange; a fit that stops at iteration t
+ * has run one extra SNP pass, which only writes the S workspace.  The whole loop is enqueued on `stream` by
+ * this call; the host polls the done flag every poll_every iterations, every rank at the same iterations.
+ *
+ * vb_comm wraps an NCCL communicator (libnccl.so.2 is bound at run time with dlopen: the library has no
+ * link-time dependency on it).  Rank 0 calls vb_comm_unique_id, the 128 bytes travel to the other ranks by any
+ * means (the Python layer uses torch.distributed), every rank calls vb_comm_create.  n_ranks == 1 needs no NCCL
+ * and no id (the same loop without the exchange: the single-GPU parity test of the deferred ELBO). */
+typedef struct vb_comm vb_comm;
+#define VB_COMM_ID_BYTES 128
+int vb_comm_unique_id(void* id_out);
+int vb_comm_create(int device, int n_ranks, int rank, const void* id, vb_comm** out);
+void vb_comm_destroy(vb_comm* c);
+/* sum-all-reduce / broadcast / all-gather of device doubles on `stream` (the model-selection step and the result
+ * gather of the sharded fit use them; NCCL over NVLink) */
+int vb_comm_allreduce(vb_comm* c, double* buf, int64_t n, void* stream);
+int vb_comm_broadcast(vb_comm* c, double* buf, int64_t n, int root, void* stream);
+int vb_comm_allgather(vb_comm* c, const double* send, double* recv, int64_t n_per_rank, void* stream);
+/* a: args of a one-restart batch (n_batch == 1, ase_mode == 0) over the LOCAL cells; xbuf: device workspace of
+ * 2 * n_var * n_donor + 8 doubles (the exchange buffer; a->S1 / a->S2 are ignored). */
+int vb_vireo_fit_sharded(const vb_counts* m_local, const vb_vireo_args* a, vb_comm* c, double* xbuf, void* stream);
+/* GT update alone over sharded cells (predict_doublet's final update_GT_prob, vireo_doublet.py:75): local SNP
+ * pass, all-reduce of S1 | S2, GT softmax. */
+int vb_vireo_gt_sharded(const vb_counts* m_local, const vb_vireo_args* a, vb_comm* c, double* xbuf, void* stream);
+
 /* Launch accounting.  Kernel classes: 0 k_snp, 1 k_theta, 2 k_gt, 3 k_cell, 4 k_elbo, 5 k_bmm_theta,
- * 6 k_terms, 7 doublet helpers.  vb_launch_counts: cumulative launches per class since load.
+ * 6 k_terms, 7 helpers (row padding, log priors, doublet tables and softmax, exchange packing).  Kernels replayed
+ * from a captured graph are counted per replay.  vb_launch_counts: cumulative launches per class since load.
  * vb_profile_enable(1) brackets every launch with CUDA events on its stream; vb_profile_read waits for
  * them, returns summed milliseconds and launch counts per class (arrays of 8) and clears the record. */
 void vb_launch_counts(int64_t* n8);
@@ -200,12 +261,13 @@ int vb_profile_read(double* ms8, int64_t* n8);
 
 /* Kernel family for the two sparse passes: 0 = automatic (window-segment kernels with FP64 tables for large
  * count matrices with n_donor <= 16, row kernels otherwise), 1 = row kernels (one warp per row, table gathered
- * from L2), 2 = gather-stream kernels (lane per row, table streamed through a shared-memory ring),
- * 3 = window-segment kernels, FP64 tables (4 lanes per row, table windows in shared memory),
+ * from L2), 3 = window-segment kernels, FP64 tables (4 lanes per row, table windows in shared memory),
  * 4 = window-segment kernels with 32-bit fixed-point tables and exact 64-bit integer accumulation (Vireo
  *     without ASE mode; < 1e-7 per update on log-likelihoods; other models use 3).
- * Process-wide; affects workspaces sized afterwards. */
+ * Process-wide.  Workspaces sized under one family and used under another are rejected (see vb_vireo_args.ws). */
 void vb_set_path(int mode);
+/* 1 (default): fits of small matrices replay captured CUDA graphs; 0: plain launches */
+void vb_set_graphs(int on);
 
 const char* vb_last_error(void);
 /* library build info: "vireo_b200 <version> sm_100a" */

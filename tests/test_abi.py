@@ -31,10 +31,56 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    # field order/size as in the header: 14 int32 + 1 double + 21 pointers; 8 int32 + 1 double + 17 pointers
-    assert ctypes.sizeof(_lib.VireoArgs) == 14 * 4 + 8 + 21 * 8
-    assert ctypes.sizeof(_lib.BmmArgs) == 8 * 4 + 8 + 17 * 8
+    # field order/size as in the header: 14 int32 + 1 double + 21 pointers + vb_ws_sizes; 8 int32 + 1 double +
+    # 17 pointers + vb_ws_sizes
     assert ctypes.sizeof(_lib.WsSizes) == 9 * 8
+    assert ctypes.sizeof(_lib.VireoArgs) == 14 * 4 + 8 + 21 * 8 + 9 * 8
+    assert ctypes.sizeof(_lib.BmmArgs) == 8 * 4 + 8 + 17 * 8 + 9 * 8
+    assert ctypes.sizeof(_lib.DoubletWs) == 3 * 8
+    assert _lib.VireoArgs.ws.offset == 14 * 4 + 8 + 21 * 8
+
+
+def test_single_rank_comm_needs_no_nccl():
+    """vb_comm with one rank: created and destroyed without NCCL and without a GPU (the sharded loop then runs without
+    its exchange step); bad ranks are rejected."""
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.vb_comm_create(0, 1, 0, None, ctypes.byref(h)) == 0 and h.value
+    lib.vb_comm_destroy(h)
+    assert lib.vb_comm_create(0, 2, 2, None, ctypes.byref(h)) != 0
+    assert lib.vb_comm_create(0, 2, 0, None, ctypes.byref(h)) != 0 and b"unique id" in lib.vb_last_error()
+
+
+def test_cache_fingerprints_cover_the_full_buffers():
+    """the staged-matrix cache and the prior cache must notice ANY in-place edit -- of values, indices or
+    index pointers, anywhere in the buffer (a strided sample misses most positions)."""
+    from scipy.sparse import random as sprandom
+    from vireo_b200 import _engine
+    rng = np.random.default_rng(0)
+    M = sprandom(3000, 2000, density=0.05, format="csc", random_state=1, data_rvs=lambda n: rng.integers(1, 9, n))
+    M.data = M.data.astype(np.int64)
+    fp0 = _engine._fingerprint(M)
+    assert _engine._fingerprint(M) == fp0
+    M.data[1] += 3                                   # the advisor's example: an entry off any sample grid
+    fp1 = _engine._fingerprint(M)
+    assert fp1 != fp0
+    M.indices[12345] ^= 1
+    fp2 = _engine._fingerprint(M)
+    assert fp2 != fp1
+    M.indptr[7] += 1
+    assert _engine._fingerprint(M) != fp2
+    big = rng.random(5_000_000)                      # large enough for the threaded path
+    c0 = _engine.checksum(big)
+    big[4_999_999] += 1e-9
+    c1 = _engine.checksum(big)
+    big[17], big[3_000_017] = big[3_000_017], big[17]          # a swap across the thread chunks
+    assert c0 != c1 and _engine.checksum(big) != c1
+    prior = np.full((400, 8, 3), 1 / 3)
+    p0 = _engine._fp_array(prior)
+    prior[137, 0, :] = [0.5, 0.25, 0.25]
+    assert _engine._fp_array(prior) != p0
+    odd = np.arange(13, dtype=np.uint8)              # buffers that are not a multiple of 8 bytes
+    assert _engine.checksum(odd) != _engine.checksum(odd[::-1].copy())
 
 
 def test_library_is_built_for_sm100a():

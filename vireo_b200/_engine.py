@@ -76,8 +76,10 @@ def _typed(a, codes):
 class StagedCounts:
     """AD and DP resident in HBM in both orientations (cell-major and SNP-major), staged once.
 
-    Takes the place of the (AD, DP) pair wherever the API accepts one: ``model.fit(staged, None)``
-    or simply ``model.fit(AD, DP)`` -- the latter stages on first use and caches by object identity.
+    Takes the place of the (AD, DP) pair wherever the API accepts one: ``model.fit(staged, None)``.
+    ``model.fit(AD, DP)`` with scipy matrices also works: it stages on first use and re-uses the copy as long as a
+    checksum over the FULL contents of both matrices still matches (see ``stage``); passing the handle skips that
+    check and is the fast path for repeated calls.
     """
 
     def __init__(self, AD, DP, device=None):
@@ -99,19 +101,33 @@ class StagedCounts:
             ad_data, dp_data = ad_data.astype(common), dp_data.astype(common)
         handle = C.c_void_p()
         ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
-        with torch().cuda.device(self.device):
-            _lib.check(lib.vb_counts_create(
-                self.device, self.n_cell, self.n_var,
-                ptr(arrs[0]), _DTYPE_CODE[np.dtype(idx_t)], ptr(arrs[1]), _DTYPE_CODE[np.dtype(idx_t)],
-                ptr(dp_data), _DTYPE_CODE[dp_data.dtype], int(DP.nnz),
-                ptr(arrs[2]), ptr(arrs[3]), ptr(ad_data), int(AD.nnz),
-                _stream(self.device), C.byref(handle)))
+        _lib.check(lib.vb_counts_create(
+            self.device, self.n_cell, self.n_var,
+            ptr(arrs[0]), _DTYPE_CODE[np.dtype(idx_t)], ptr(arrs[1]), _DTYPE_CODE[np.dtype(idx_t)],
+            ptr(dp_data), _DTYPE_CODE[dp_data.dtype], int(DP.nnz),
+            ptr(arrs[2]), ptr(arrs[3]), ptr(ad_data), int(AD.nnz),
+            _stream(self.device), C.byref(handle)))
+        self._adopt(handle, np.asarray(DP.indptr, dtype=np.int64).copy())
+
+    def _adopt(self, handle, indptr):
+        lib = _lib.load()
         self._h = handle
+        self.indptr = indptr                       # nnz offsets of the cells (host copy: shard bounds are cut by nnz)
         self.nnz = int(lib.vb_counts_info(handle, 2))
         self.wide = bool(lib.vb_counts_info(handle, 3))
         self.bytes = int(lib.vb_counts_info(handle, 5))
         self._binom = None
+        self._pool = {}                            # workspaces of finished batches, re-used by the next one
+        self._shards = {}                          # (world, rank) -> (StagedCounts of this rank's cells, c0, c1, bounds)
+        self._warned = False
         self._finalizer = weakref.finalize(self, lib.vb_counts_destroy, handle)
+
+    @classmethod
+    def _from_handle(cls, handle, device, n_var, n_cell, indptr):
+        self = cls.__new__(cls)
+        self.device, self.n_var, self.n_cell = device, n_var, n_cell
+        self._adopt(handle, indptr)
+        return self
 
     # (n_var, n_cell), like the matrices it replaces
     @property
@@ -125,16 +141,38 @@ class StagedCounts:
         return self._h
 
     def close(self):
+        for sh in self._shards.values():
+            sh[0].close()
+        self._shards = {}
+        self._pool = {}
         if self._h is not None:
             self._finalizer()
             self._h = None
+
+    def slice_cells(self, c0, c1):
+        """StagedCounts of the cells [c0, c1), cut on the device from the resident arrays (no host traffic)."""
+        out = C.c_void_p()
+        _lib.check(_lib.load().vb_counts_slice(self.handle, int(c0), int(c1), _stream(self.device), C.byref(out)))
+        return StagedCounts._from_handle(out, self.device, self.n_var, int(c1 - c0),
+                                         (self.indptr[c0:c1 + 1] - self.indptr[c0]).copy())
+
+    def check_family(self):
+        """Say so (once) when the automatic selector had to fall back to the row kernels because building the
+        window-segment formats FAILED -- the fit is then several times slower on a large matrix."""
+        if not self._warned and int(_lib.load().vb_counts_info(self.handle, 60)) == 2:
+            self._warned = True
+            note = _lib.load().vb_counts_note(self.handle)
+            import warnings
+            warnings.warn("vireo_b200: the window-segment formats could not be built (%s); falling back to the row "
+                          "kernels, which are several times slower on large matrices"
+                          % (note.decode() if note else "?"), RuntimeWarning, stacklevel=3)
 
     def binom_const(self):
         """float32 sum over nnz of min(log C(dp, ad), 700): the constant ``Vireo.fit`` adds to the ELBO
         (reference vireoSNP/utils/vireo_base.py:7-22, vireo_model.py:313), computed on the device."""
         if self._binom is None:
             t = torch()
-            scratch = t.empty(1024, dtype=t.float64, device=self.device)
+            scratch = t.empty(1024, dtype=t.float64, device="cuda:%d" % self.device)
             out = C.c_double()
             _lib.check(_lib.load().vb_binom_const(self.handle, C.c_void_p(scratch.data_ptr()), C.byref(out),
                                                   _stream(self.device)))
@@ -144,23 +182,55 @@ class StagedCounts:
 
 _CACHE = {}
 _CACHE_MAX = 4
+_HASH_POOL = None
+
+
+def checksum(a):
+    """64-bit sum over the FULL buffer of an array (modular arithmetic on its bytes viewed as uint64/uint8): any
+    single-element edit changes it.  Large buffers are summed by a few threads (numpy releases the GIL)."""
+    a = np.asarray(a)
+    if a.size == 0:
+        return 0
+    if not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a)
+    raw = a.reshape(-1).view(np.uint8)
+    n8 = raw.size // 8 * 8
+    words = raw[:n8].view(np.uint64)
+    tail = int(raw[n8:].astype(np.uint64).sum()) if n8 < raw.size else 0
+    if words.size < (1 << 21):
+        total = int(np.add.reduce(words)) if words.size else 0
+    else:
+        global _HASH_POOL
+        if _HASH_POOL is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _HASH_POOL = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1))
+        parts = np.array_split(words, 16)
+        # position-weighted per part, so that moving a value between parts is seen as well
+        total = sum((i + 1) * int(x) for i, x in enumerate(_HASH_POOL.map(np.add.reduce, parts)))
+    return (total + tail) & 0xFFFFFFFFFFFFFFFF
 
 
 def _fingerprint(M):
+    """Identity of the CONTENTS of a count matrix: shape, layout and full checksums of every buffer (values, indices
+    and index pointers) -- an in-place edit anywhere invalidates a cached device copy."""
     if isinstance(M, np.ndarray):
-        return ("dense", M.shape, M.ctypes.data, float(M.ravel()[:: max(1, M.size // 1024)].sum()))
-    data = M.data
-    step = max(1, data.size // 1024)
-    index = getattr(M, "indices", None)
-    if index is None:
-        index = getattr(M, "row", data)
-    return (M.format, M.shape, int(M.nnz), data.ctypes.data, index.ctypes.data,
-            float(data[::step].sum()) if data.size else 0.0)
+        return ("dense", M.shape, M.dtype.str, checksum(M))
+    parts = [M.format, M.shape, int(M.nnz), M.data.dtype.str, checksum(M.data)]
+    for name in ("indices", "indptr", "row", "col", "offsets"):
+        arr = getattr(M, name, None)
+        if arr is not None:
+            parts.append(checksum(arr))
+    return tuple(parts)
 
 
 def stage(AD, DP=None, device=None):
-    """Return the StagedCounts for (AD, DP), staging on first use.  Cached by object identity plus a
-    cheap fingerprint, so repeated ``fit`` calls on the same matrices upload nothing."""
+    """Return the StagedCounts for (AD, DP), staging on first use.
+
+    A staged copy is re-used for the same two matrix objects only if a checksum over the full contents of both
+    still matches, so an in-place edit of ``.data``, ``.indices`` or ``.indptr`` between two calls is always picked
+    up (the reference reads the live matrices on every call).  The check reads both matrices once (tens of
+    milliseconds at 1e8 nnz); callers that fit the same matrices repeatedly should stage once and pass the handle:
+    ``counts = vireo_b200.stage(AD, DP); model.fit(counts, None)``."""
     if isinstance(AD, StagedCounts):
         return AD
     dev = default_device() if device is None else int(device)
@@ -169,8 +239,8 @@ def stage(AD, DP=None, device=None):
     hit = _CACHE.get(key)
     if hit is not None and hit[0] == fp and hit[1]._h is not None:
         return hit[1]
-    staged = StagedCounts(AD, DP, dev)
-    if len(_CACHE) >= _CACHE_MAX:
+    staged = StagedCounts(AD, DP, dev)          # a stale copy is simply dropped (freed when nothing refers to it)
+    if len(_CACHE) >= _CACHE_MAX and key not in _CACHE:
         _CACHE.pop(next(iter(_CACHE)))
     _CACHE[key] = (fp, staged)
     try:   # drop the entry when either matrix is garbage collected (ids get recycled)
@@ -201,25 +271,17 @@ def _dev(arr, device):
     return t.from_numpy(a).to("cuda:%d" % device)
 
 
-_PINNED_UP = {}
-
-
-def _stage_up(shape, device, fill):
-    """Host -> device through a reused pinned buffer: `fill(view)` writes the float64 payload straight into the
-    pinned staging area (one host pass instead of a temporary plus a pageable copy), then one DMA."""
+def _upload_into(dst, arr, shape):
+    """Host array (broadcast to `shape`) -> the device view `dst`, ONE asynchronous copy and no staging pass on the
+    host: arrays this package handed out live in pinned memory (see ``_to_host``) and go by DMA; anything else is
+    staged by the driver, and ``cudaMemcpyAsync`` returns once a pageable source has been consumed."""
     t = torch()
-    n = int(np.prod(shape))
-    buf = _PINNED_UP.get(n)
-    if buf is None:
-        if len(_PINNED_UP) > 16:
-            _PINNED_UP.clear()
-        buf = t.empty(max(n, 1), dtype=t.float64, pin_memory=True)
-        _PINNED_UP[n] = buf
-    fill(buf.numpy()[:n].reshape(shape))
-    out = t.empty(max(n, 1), dtype=t.float64, device="cuda:%d" % device)
-    out[:n].copy_(buf[:n], non_blocking=True)
-    t.cuda.current_stream(device).synchronize()      # the staging buffer is reused by the next upload
-    return out
+    a = np.asarray(arr, dtype=np.float64)
+    if a.shape != tuple(shape):
+        a = np.broadcast_to(a, shape)
+    if not (a.flags.c_contiguous and a.flags.writeable):
+        a = np.array(a, dtype=np.float64, order="C")
+    dst.copy_(t.from_numpy(a).reshape(-1), non_blocking=True)
 
 
 def _zeros(n, device, dtype=None):
@@ -244,24 +306,15 @@ def _log_prior_pair(prior, device):
     return raw, norm
 
 
-_PINNED = {}
-
-
 def _to_host(tensor):
-    """Device tensor -> fresh numpy array, through a reused pinned staging buffer (pageable
-    device-to-host copies run at a fraction of the link rate)."""
+    """Device tensor -> numpy array that LIVES in pinned memory: one DMA, no second host copy.  The pinned block
+    comes from PyTorch's caching host allocator and returns to it when the array is garbage collected."""
     t = torch()
     n = tensor.numel()
-    key = (n, tensor.dtype)
-    buf = _PINNED.get(key)
-    if buf is None:
-        if len(_PINNED) > 16:
-            _PINNED.clear()
-        buf = t.empty(n, dtype=tensor.dtype, pin_memory=True)
-        _PINNED[key] = buf
-    buf.copy_(tensor.reshape(-1), non_blocking=True)
+    buf = t.empty(max(n, 1), dtype=tensor.dtype, pin_memory=True)
+    buf[:n].copy_(tensor.reshape(-1), non_blocking=True)
     t.cuda.current_stream(tensor.device).synchronize()
-    return buf.numpy().copy().reshape(tuple(tensor.shape))
+    return buf.numpy()[:n].reshape(tuple(tensor.shape))
 
 
 def _compress_rows(a):
@@ -303,16 +356,14 @@ _PRIORS = {}
 
 def _fp_array(a):
     a = np.asarray(a)
-    flat = a.reshape(-1) if a.flags.c_contiguous else a.ravel()
-    step = max(1, flat.size // 2048)
-    return (a.shape, a.dtype.str, a.ctypes.data, float(flat[::step].sum()) if flat.size else 0.0,
-            float(flat[0]) if flat.size else 0.0, float(flat[-1]) if flat.size else 0.0)
+    return (a.shape, a.dtype.str, checksum(a))
 
 
 def _vireo_priors(m0, dev, C_, V, K, G, T):
     """Device-side priors of a Vireo model: logs of the donor and genotype priors (both flavours, see
-    ``_log_prior_pair``) and the theta prior.  They are constants of the model like the count matrices, so they are
-    cached the same way (object identity plus a sampled fingerprint): repeated fits of one model upload its state only."""
+    ``_log_prior_pair``) and the theta prior.  They are constants of the model like the count matrices, so the
+    device copies are re-used while a checksum over the FULL contents of every prior array still matches
+    (an in-place edit such as ``model.GT_prior[i, 0, :] = ...`` is always picked up)."""
     arrs = (m0.ID_prior, m0.GT_prior, m0.theta_s1_prior, m0.theta_s2_prior)
     key = tuple(id(a) for a in arrs) + (dev, C_, V, K, G, T)
     fp = tuple(_fp_array(a) for a in arrs)
@@ -349,6 +400,36 @@ def _vireo_priors(m0, dev, C_, V, K, G, T):
     return out
 
 
+_WS_FIELDS = ("S", "W", "loglik", "ab", "part", "scal", "ctrl", "rpad", "heavy")
+
+
+def _acquire_ws(counts, kind, K, G, B, ase, sizes_fn):
+    """Workspaces (and the state buffer) of a batch on `counts`: taken from the handle's pool when a finished batch of
+    the same geometry left them there, so that repeated fits allocate nothing.  The pool key includes the kernel
+    family the sizes were computed for."""
+    t = torch()
+    dev = counts.device
+    ws = _lib.WsSizes()
+    _lib.check(sizes_fn(ws))
+    counts.check_family()
+    key = (kind, K, G, B, ase) + tuple(int(getattr(ws, f)) for f in _WS_FIELDS)
+    free = counts._pool.get(key)
+    if free:
+        return key, ws, free.pop()
+    bufs = {"S12": _zeros(2 * ws.S, dev), "W": _zeros(ws.W, dev), "loglik": _zeros(ws.loglik, dev),
+            "ab": _zeros(ws.ab, dev), "part": _zeros(ws.part, dev), "scal": _zeros(ws.scal, dev),
+            "ctrl": _zeros(ws.ctrl, dev, t.int32), "rpad": _zeros(ws.rpad, dev), "heavy": _zeros(ws.heavy, dev)}
+    return key, ws, bufs
+
+
+def _release_ws(counts, key, bufs):
+    if counts._h is None:
+        return
+    free = counts._pool.setdefault(key, [])
+    if len(free) < 2:
+        free.append(bufs)
+
+
 class VireoBatch:
     """Device state of B Vireo restarts that share shapes, flags and priors."""
 
@@ -370,40 +451,54 @@ class VireoBatch:
         T = V if self.ase else 1
         self.T = T
         t = torch()
+        lib = _lib.load()
 
-        def stack(name, shape):
-            def fill(out):
-                for i, m in enumerate(self.models):
-                    out[i] = np.broadcast_to(np.asarray(getattr(m, name), dtype=np.float64), shape)
-            return _stage_up((B,) + shape, dev, fill)
-
-        self.id_prob = stack("ID_prob", (C_, K))
-        self.gt_prob = stack("GT_prob", (V, K, G))
-        self.beta_mu = stack("beta_mu", (T, G))
-        self.beta_sum = stack("beta_sum", (T, G))
+        with t.cuda.device(dev):
+            self._key, self.ws, bufs = _acquire_ws(
+                counts, "vireo", K, G, B, int(self.ase),
+                lambda ws: lib.vb_vireo_ws_sizes(counts.handle, K, G, B, int(self.ase), _stream(dev), C.byref(ws)))
+        self._bufs = bufs
+        # state of the batch in ONE allocation: ID_prob | GT_prob | beta_mu | beta_sum (one download brings all of it)
+        n_id, n_gt, n_th = B * C_ * K, B * V * K * G, B * T * G
+        if "state" not in bufs or bufs["state"].numel() != n_id + n_gt + 2 * n_th:
+            bufs["state"] = t.empty(max(n_id + n_gt + 2 * n_th, 1), dtype=t.float64, device="cuda:%d" % dev)
+        st = bufs["state"]
+        self.state = st
+        self.id_prob, self.gt_prob = st[:n_id], st[n_id:n_id + n_gt]
+        self.beta_mu, self.beta_sum = st[n_id + n_gt:n_id + n_gt + n_th], st[n_id + n_gt + n_th:n_id + n_gt + 2 * n_th]
+        for i, m in enumerate(self.models):
+            _upload_into(self.id_prob[i * C_ * K:(i + 1) * C_ * K], m.ID_prob, (C_, K))
+            _upload_into(self.gt_prob[i * V * K * G:(i + 1) * V * K * G], m.GT_prob, (V, K, G))
+            _upload_into(self.beta_mu[i * T * G:(i + 1) * T * G], m.beta_mu, (T, G))
+            _upload_into(self.beta_sum[i * T * G:(i + 1) * T * G], m.beta_sum, (T, G))
 
         pri = _vireo_priors(m0, dev, C_, V, K, G, T)
         self.id_rows, self.thp_rows = pri["id_rows"], pri["thp_rows"]
         self.lidp, self.lidp_kl, self.lgtp, self.lgtp_kl = pri["lidp"], pri["lidp_kl"], pri["lgtp"], pri["lgtp_kl"]
         self.s1p, self.s2p = pri["s1p"], pri["s2p"]
 
-        ws = _lib.WsSizes()
-        _lib.check(_lib.load().vb_vireo_ws_sizes(counts.handle, K, G, B, int(self.ase), C.byref(ws)))
-        self.S12 = _zeros(2 * ws.S, dev)          # S1 | S2 in one allocation: the cell-sharded fit all-reduces both at once
-        self.S1, self.S2 = self.S12[:ws.S], self.S12[ws.S:]
-        self.W = _zeros(ws.W, dev)
-        self.loglik = _zeros(ws.loglik, dev)
-        self.ab = _zeros(ws.ab, dev)
-        self.part = _zeros(ws.part, dev)
-        self.scal = _zeros(ws.scal, dev)
-        self.ctrl = _zeros(ws.ctrl, dev, t.int32)
-        self.rpad = _zeros(ws.rpad, dev)
-        self.heavy = _zeros(ws.heavy, dev)
-        self.elbo = None
+        self.S12 = bufs["S12"]                    # S1 | S2 in one allocation
+        half = self.S12.numel() // 2
+        self.S1, self.S2 = self.S12[:half], self.S12[half:]
+        for name in ("W", "loglik", "ab", "part", "scal", "ctrl", "rpad", "heavy"):
+            setattr(self, name, bufs[name])
+        self.elbo = bufs.get("elbo")
+
+    def close(self):
+        """Hand the workspaces back to the pool of the staged matrices (also done when the batch is collected)."""
+        if self._bufs is not None:
+            self._bufs["elbo"] = self.elbo
+            _release_ws(self.counts, self._key, self._bufs)
+            self._bufs = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def args(self, max_iter=1, min_iter=0, eps=1e-2, delay=0, poll_every=0):
         m0 = self.models[0]
-        t = torch()
         if self.elbo is None or self.elbo.numel() != self.B * max_iter:
             self.elbo = _zeros(self.B * max_iter, self.dev)
         a = _lib.VireoArgs()
@@ -419,21 +514,19 @@ class VireoBatch:
         a.log_id_prior, a.log_id_prior_kl = self.lidp.data_ptr(), self.lidp_kl.data_ptr()
         a.log_gt_prior, a.log_gt_prior_kl = self.lgtp.data_ptr(), self.lgtp_kl.data_ptr()
         a.s1_prior, a.s2_prior = self.s1p.data_ptr(), self.s2p.data_ptr()
-        del t
+        a.ws = self.ws
         return a
 
     # -- device runs -------------------------------------------------------------------------
     def run_fit(self, max_iter, min_iter, eps, delay, poll_every=0):
         """max_iter EM iterations (or fewer if every restart converges) on the device; no host copies."""
         a = self.args(max_iter, min_iter, eps, delay, poll_every)
-        with torch().cuda.device(self.dev):
-            _lib.check(_lib.load().vb_vireo_fit(self.counts.handle, C.byref(a), _stream(self.dev)))
+        _lib.check(_lib.load().vb_vireo_fit(self.counts.handle, C.byref(a), _stream(self.dev)))
         self.max_iter = max_iter
 
     def run_step(self, phases):
         a = self.args()
-        with torch().cuda.device(self.dev):
-            _lib.check(_lib.load().vb_vireo_step(self.counts.handle, C.byref(a), int(phases), _stream(self.dev)))
+        _lib.check(_lib.load().vb_vireo_step(self.counts.handle, C.byref(a), int(phases), _stream(self.dev)))
 
     # -- results -----------------------------------------------------------------------------
     def traces(self):
@@ -445,18 +538,26 @@ class VireoBatch:
     def download(self, what=("ID_prob", "GT_prob", "theta")):
         host = {}
         B, C_, V, K, G, T = self.B, self.C, self.V, self.K, self.G, self.T
-        if "ID_prob" in what:
-            host["ID_prob"] = _to_host(self.id_prob).reshape(B, C_, K)
-        if "GT_prob" in what:
-            host["GT_prob"] = _to_host(self.gt_prob).reshape(B, V, K, G)
-        if "theta" in what:
-            host["beta_mu"] = _to_host(self.beta_mu).reshape(B, T, G)
-            host["beta_sum"] = _to_host(self.beta_sum).reshape(B, T, G)
+        if "ID_prob" in what and "GT_prob" in what and "theta" in what:
+            full = _to_host(self.state)                         # one DMA for the whole state
+            n_id, n_gt, n_th = B * C_ * K, B * V * K * G, B * T * G
+            host["ID_prob"] = full[:n_id].reshape(B, C_, K)
+            host["GT_prob"] = full[n_id:n_id + n_gt].reshape(B, V, K, G)
+            host["beta_mu"] = full[n_id + n_gt:n_id + n_gt + n_th].reshape(B, T, G)
+            host["beta_sum"] = full[n_id + n_gt + n_th:n_id + n_gt + 2 * n_th].reshape(B, T, G)
+        else:
+            if "ID_prob" in what:
+                host["ID_prob"] = _to_host(self.id_prob).reshape(B, C_, K)
+            if "GT_prob" in what:
+                host["GT_prob"] = _to_host(self.gt_prob).reshape(B, V, K, G)
+            if "theta" in what:
+                th = _to_host(self.state[B * C_ * K + B * V * K * G:])
+                host["beta_mu"], host["beta_sum"] = th[:B * T * G].reshape(B, T, G), th[B * T * G:].reshape(B, T, G)
         for b, m in enumerate(self.models):
             if "ID_prob" in host:
-                m.ID_prob = host["ID_prob"][b].copy() if self.B > 1 else host["ID_prob"][b]
+                m.ID_prob = host["ID_prob"][b]
             if "GT_prob" in host:
-                m.GT_prob = host["GT_prob"][b].copy() if self.B > 1 else host["GT_prob"][b]
+                m.GT_prob = host["GT_prob"][b]
             if "beta_mu" in host:
                 m.beta_mu = host["beta_mu"][b].copy()
                 m.beta_sum = host["beta_sum"][b].copy()
@@ -479,6 +580,7 @@ def vireo_fit_models(counts, models, max_iter, min_iter, epsilon_conv, delay_fit
     for (elbo, last), m in zip(batch.traces(), models):
         replay_convergence(elbo, last, max_iter, min_iter, epsilon_conv, False, verbose)
         out.append(elbo[:last].copy())
+    batch.close()
     return out
 
 
@@ -522,7 +624,9 @@ class BmmBatch:
         self.s1p = _dev(np.broadcast_to(np.asarray(model.theta_s1_prior, dtype=np.float64), (V, K)), dev)
         self.s2p = _dev(np.broadcast_to(np.asarray(model.theta_s2_prior, dtype=np.float64), (V, K)), dev)
         ws = _lib.WsSizes()
-        _lib.check(_lib.load().vb_bmm_ws_sizes(counts.handle, K, B, C.byref(ws)))
+        _lib.check(_lib.load().vb_bmm_ws_sizes(counts.handle, K, B, _stream(dev), C.byref(ws)))
+        counts.check_family()
+        self.ws = ws
         self.S1, self.S2 = _zeros(ws.S, dev), _zeros(ws.S, dev)
         self.W = _zeros(ws.W, dev)
         self.loglik = _zeros(ws.loglik, dev)
@@ -544,18 +648,17 @@ class BmmBatch:
             setattr(a, name, getattr(self, name).data_ptr())
         a.log_id_prior, a.log_id_prior_kl = self.lidp.data_ptr(), self.lidp_kl.data_ptr()
         a.s1_prior, a.s2_prior = self.s1p.data_ptr(), self.s2p.data_ptr()
+        a.ws = self.ws
         return a
 
     def run_fit(self, max_iter, min_iter, eps, poll_every=0):
         a = self.args(max_iter, min_iter, eps, poll_every)
-        with torch().cuda.device(self.dev):
-            _lib.check(_lib.load().vb_bmm_fit(self.counts.handle, C.byref(a), _stream(self.dev)))
+        _lib.check(_lib.load().vb_bmm_fit(self.counts.handle, C.byref(a), _stream(self.dev)))
         self.max_iter = max_iter
 
     def run_step(self, phases):
         a = self.args()
-        with torch().cuda.device(self.dev):
-            _lib.check(_lib.load().vb_bmm_step(self.counts.handle, C.byref(a), int(phases), _stream(self.dev)))
+        _lib.check(_lib.load().vb_bmm_step(self.counts.handle, C.byref(a), int(phases), _stream(self.dev)))
 
     def traces(self):
         ctrl = self.ctrl.cpu().numpy().reshape(self.B, _lib.CTRL_N)
@@ -576,20 +679,26 @@ class BmmBatch:
 # doublet pass
 # ---------------------------------------------------------------------------------------------
 
-def doublet_pass(counts, GT_prob, beta_mu, beta_sum, log_prior_both, ase, want_loglik=False):
-    """logLik over singlet + donor-pair columns, softmax with the doublet prior, LLR -- all on the device."""
+def doublet_pass(counts, GT_prob, beta_mu, beta_sum, log_prior_both, ase, want_loglik=False, keep_device=False):
+    """logLik over singlet + donor-pair columns, softmax with the doublet prior, LLR -- all on the device.
+    Returns (loglik or None, posterior over all K2 columns, LLR) as host arrays, or the device tensors (posterior, LLR)
+    when ``keep_device`` (the sharded wrapper gathers them across ranks before the download)."""
     dev = counts.device
+    lib = _lib.load()
     V, K, G = GT_prob.shape
     K2 = K + K * (K - 1) // 2
     lp = np.asarray(log_prior_both, dtype=np.float64)
     lp = _compress_rows(lp)
     gt, mu, sm, lpd = _dev(GT_prob, dev), _dev(beta_mu, dev), _dev(beta_sum, dev), _dev(lp, dev)
-    W = _zeros(2 * V * K2, dev)
+    ws = _lib.DoubletWs()
+    _lib.check(lib.vb_doublet_ws_sizes(counts.handle, K, G, int(bool(ase)), _stream(dev), C.byref(ws)))
+    W, heavy, ab2 = _zeros(ws.W, dev), _zeros(ws.heavy, dev), _zeros(ws.ab2, dev)
     ll, pr, llr = _zeros(counts.n_cell * K2, dev), _zeros(counts.n_cell * K2, dev), _zeros(counts.n_cell, dev)
-    with torch().cuda.device(dev):
-        _lib.check(_lib.load().vb_vireo_doublet(counts.handle, K, G, int(bool(ase)), _ptr(gt), _ptr(mu), _ptr(sm),
-                                                _ptr(lpd), lp.shape[0], _ptr(W), _ptr(ll), _ptr(pr),
-                                                _ptr(llr), _stream(dev)))
+    _lib.check(lib.vb_vireo_doublet(counts.handle, K, G, int(bool(ase)), _ptr(gt), _ptr(mu), _ptr(sm),
+                                    _ptr(lpd), lp.shape[0], _ptr(W), _ptr(heavy), _ptr(ab2), C.byref(ws),
+                                    _ptr(ll), _ptr(pr), _ptr(llr), _stream(dev)))
     C_ = counts.n_cell
+    if keep_device:
+        return pr, llr
     # the log-likelihoods stay on the device (109 MB at cfg3; no caller reads them): posterior and LLR only
     return (None if not want_loglik else _to_host(ll).reshape(C_, K2), _to_host(pr).reshape(C_, K2), _to_host(llr))

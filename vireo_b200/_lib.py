@@ -34,7 +34,12 @@ class VireoArgs(C.Structure):
         ("s1_prior", c_dp), ("s2_prior", c_dp),
         ("S1", c_dp), ("S2", c_dp), ("W", c_dp), ("loglik", c_dp), ("ab", c_dp), ("part", c_dp),
         ("scal", c_dp), ("ctrl", c_dp), ("elbo", c_dp), ("rpad", c_dp), ("heavy", c_dp),
+        ("ws", WsSizes),
     ]
+
+
+class DoubletWs(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("W", "heavy", "ab2")]
 
 
 class BmmArgs(C.Structure):
@@ -46,8 +51,11 @@ class BmmArgs(C.Structure):
         ("log_id_prior", c_dp), ("log_id_prior_kl", c_dp), ("s1_prior", c_dp), ("s2_prior", c_dp),
         ("S1", c_dp), ("S2", c_dp), ("W", c_dp), ("loglik", c_dp), ("part", c_dp),
         ("scal", c_dp), ("ctrl", c_dp), ("elbo", c_dp), ("rpad", c_dp), ("heavy", c_dp),
+        ("ws", WsSizes),
     ]
 
+
+COMM_ID_BYTES = 128
 
 # every symbol include/vireo_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -55,18 +63,30 @@ SIGNATURES = {
                                    C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.POINTER(C.c_void_p)]),
     "vb_counts_destroy": (None, [C.c_void_p]),
+    "vb_counts_slice": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),
     "vb_counts_info": (C.c_int64, [C.c_void_p, C.c_int]),
+    "vb_counts_note": (C.c_char_p, [C.c_void_p]),
     "vb_binom_const": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
-    "vb_vireo_ws_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(WsSizes)]),
+    "vb_vireo_ws_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(WsSizes)]),
     "vb_log_prior": (C.c_int, [c_dp, C.c_int64, C.c_int, c_dp, c_dp, C.c_void_p]),
     "vb_vireo_fit": (C.c_int, [C.c_void_p, C.POINTER(VireoArgs), C.c_void_p]),
     "vb_vireo_step": (C.c_int, [C.c_void_p, C.POINTER(VireoArgs), C.c_int, C.c_void_p]),
-    "vb_bmm_ws_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(WsSizes)]),
+    "vb_bmm_ws_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(WsSizes)]),
     "vb_bmm_fit": (C.c_int, [C.c_void_p, C.POINTER(BmmArgs), C.c_void_p]),
     "vb_bmm_step": (C.c_int, [C.c_void_p, C.POINTER(BmmArgs), C.c_int, C.c_void_p]),
+    "vb_doublet_ws_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(DoubletWs)]),
     "vb_vireo_doublet": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_int,
-                                   c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
+                                   c_dp, c_dp, c_dp, C.POINTER(DoubletWs), c_dp, c_dp, c_dp, C.c_void_p]),
+    "vb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "vb_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "vb_comm_destroy": (None, [C.c_void_p]),
+    "vb_comm_allreduce": (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_void_p]),
+    "vb_comm_broadcast": (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_int, C.c_void_p]),
+    "vb_comm_allgather": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int64, C.c_void_p]),
+    "vb_vireo_fit_sharded": (C.c_int, [C.c_void_p, C.POINTER(VireoArgs), C.c_void_p, c_dp, C.c_void_p]),
+    "vb_vireo_gt_sharded": (C.c_int, [C.c_void_p, C.POINTER(VireoArgs), C.c_void_p, c_dp, C.c_void_p]),
     "vb_set_path": (None, [C.c_int]),
+    "vb_set_graphs": (None, [C.c_int]),
     "vb_launch_counts": (None, [C.POINTER(C.c_int64)]),
     "vb_profile_enable": (None, [C.c_int]),
     "vb_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -79,7 +99,7 @@ SIGNATURES = {
 }
 
 _lib = None
-PATHS = {"auto": 0, "rows": 1, "gather": 2, "seg": 3, "seg32": 4}
+PATHS = {"auto": 0, "rows": 1, "seg": 3, "seg32": 4}
 
 
 class VireoB200Error(RuntimeError):
@@ -102,15 +122,16 @@ def load():
     _lib = lib
     env = os.environ.get("VIREO_B200_PATH", "auto").lower()
     lib.vb_set_path(PATHS.get(env, 0))
+    lib.vb_set_graphs(0 if os.environ.get("VIREO_B200_GRAPHS", "1") == "0" else 1)
     return lib
 
 
 def set_path(mode):
-    """'auto' | 'rows' | 'gather' | 'seg' | 'seg32': kernel family of the two sparse passes (see vb_set_path)."""
+    """'auto' | 'rows' | 'seg' | 'seg32': kernel family of the two sparse passes (see vb_set_path)."""
     load().vb_set_path(PATHS[mode])
 
 
-KERNEL_CLASSES = ("k_snp", "k_theta", "k_gt", "k_cell", "k_elbo", "k_bmm_theta", "k_terms", "doublet")
+KERNEL_CLASSES = ("k_snp", "k_theta", "k_gt", "k_cell", "k_elbo", "k_bmm_theta", "k_terms", "helpers")
 
 
 def launch_counts():

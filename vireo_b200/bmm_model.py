@@ -131,8 +131,8 @@ class BinomMixtureVB():
         ``max_iter`` more, add the binomial constant.
 
         The restarts consume the numpy RNG in the reference's order (one ``rand(n_cell, n_donor)`` per
-        restart, bmm_model.py:80-83) and then run together as one device batch; with
-        ``torch.distributed`` initialised they are sharded round-robin over the ranks first.
+        restart, bmm_model.py:80-83) and then run together as one device batch; after
+        ``vireo_b200.dist.enable()`` they are sharded round-robin over the ranks first.
         ``kwargs``: min_iter, epsilon_conv, verbose for the inner loop."""
         if random_seed is not None:
             np.random.seed(random_seed)
@@ -147,7 +147,9 @@ class BinomMixtureVB():
         const = counts.binom_const()
 
         starts = [self._draw_state(self.beta_mu_init, self.beta_sum_init, self.ID_prob_init) for _ in range(n_init)]
-        from .dist import shard_restarts, gather_restarts
+        from .dist import check_same_problem, gather_restarts, shard_restarts
+        check_same_problem(counts.n_cell, counts.n_var, counts.nnz, self.n_donor, n_init, random_seed, float(const),
+                           device=counts.device)
         mine = shard_restarts(n_init)
         results = {}
         if mine:

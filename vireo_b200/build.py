@@ -11,7 +11,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("vb_stage.cu", "vb_em.cu", "vb_gather.cu", "vb_seg.cu")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("vb_stage.cu", "vb_em.cu", "vb_seg.cu")]
 DEPS = SRC + [os.path.join(HERE, "csrc", "vb_common.cuh"), os.path.join(HERE, "csrc", "vb_stream.cuh"),
               os.path.join(os.path.dirname(HERE), "include", "vireo_b200.h")]
 LIB = os.path.join(HERE, "libvireo_b200.so")
@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", "-shared",
-           "-Xptxas", "-v" if verbose else "-O3", "-o", LIB, *SRC]
+           "-Xptxas", "-v" if verbose else "-O3", "-o", LIB, *SRC, "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

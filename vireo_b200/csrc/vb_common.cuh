@@ -20,64 +20,17 @@
 #define VB_SCAL_N 8   // {ELBO, LB_p, KL_ID, KL_GT, KL_theta, -, -, -}
 
 // ----------------------------------------------------------------------------------------------
-// Gather-stream format ("ring-slab gather kernels"), one per pass orientation:
+// Gather tables: both sparse passes are "for every owner row: sum over its pairs of count * table[gather row]"
 //     cell pass (A): owner = cell j,            gather row = 2*snp + allele  (rows of the W table)
 //     SNP  pass (B): owner = 2*snp + allele,    gather row = cell j          (rows of ID_prob)
 //   with allele 0 = reference reads (count dp-ad), allele 1 = alternative reads (count ad).
-//   Every (owner, gather row, count) with 1 <= count <= 31 is one 16-bit record
-//       bits 15..5  delta = gather row - gather row of the owner's previous record (first: - 0)
-//       bits  4..0  count (0 = "skip": advance `delta` rows, add nothing; bridges gaps > 2047)
-//   An owner's records form a stream in ascending gather-row order.  Owners are sorted by stream
-//   length (descending) and packed 32 to a warp slot; a warp slot's streams are interleaved in
-//   256-byte blocks [block][lane][4 records] so that lanes running in step read coalesced.
-//   Counts >= 32 go to a small residual CSR ("heavy" records) handled by k_heavy.
 // ----------------------------------------------------------------------------------------------
-#define VB_REC_COUNT_BITS 5
-#define VB_REC_MAX_COUNT 31
-#define VB_REC_MAX_DELTA 2047
-#define VB_ROW_DOUBLES 16                 // every gather-table row is 16 doubles = 128 bytes (all 32 banks)
-#define VB_SLAB_ROWS 128                  // rows per bulk copy (16 KB)
-#define VB_RING_SLABS 12                  // slabs resident in shared memory (192 KB)
-#define VB_RING_ROWS (VB_SLAB_ROWS * VB_RING_SLABS)
-#define VB_GATHER_MAX_WARPS 24            // consumer warps per CTA (+1 producer warp): 800 threads x 80 registers
-#define VB_SPARSE_LEN 64                  // streams this short may be routed to the residual kernel
-
-struct GatherSet {
-    int built;
-    int64_t n_owner, n_gather;
-    int64_t n_slot;          // warp slots = ceil(n_owner / 32)
-    int64_t n_rec;           // stream records incl. skips (excl. padding)
-    int64_t n_light;         // (owner, gather row) pairs carried by the streams
-    int64_t n_heavy;         // pairs in the residual
-    int64_t n_block;         // 256-byte stream blocks
-    int32_t* perm;           // [n_slot*32] owner id of each lane, -1 = padding
-    uint32_t* len;           // [n_slot*32] stream length of each lane
-    uint32_t* slot_blk;      // [n_slot+1] first block of each warp slot
-    uint16_t* rec;           // [n_block*128]
-    int64_t* hptr;           // [n_owner+1] residual CSR
-    int32_t* hrow;
-    uint32_t* hcnt;
-    int32_t* cta_start;      // [grid+1] first warp slot of each CTA (contiguous ranges, balanced by records)
-    int grid, max_warps;
-    int64_t bytes;
-};
-
-struct GatherView {
-    int64_t n_owner, n_gather, n_slot;
-    const int32_t* __restrict__ perm;
-    const uint32_t* __restrict__ len;
-    const uint32_t* __restrict__ slot_blk;
-    const uint16_t* __restrict__ rec;
-    const int64_t* __restrict__ hptr;
-    const int32_t* __restrict__ hrow;
-    const uint32_t* __restrict__ hcnt;
-    const int32_t* __restrict__ cta_start;
-};
-
+#define VB_ROW_DOUBLES 16                 // a full gather-table row is 16 doubles = 128 bytes (all 32 banks)
+#define VB_SPARSE_LEN 64                  // owners with this few pairs may be routed to the residual kernel
 
 // ----------------------------------------------------------------------------------------------
 // Window-segment format (vb_seg.cu), one per pass orientation and table precision.
-//   Same (owner, gather row, count) pairs as above.  The gather table is cut into windows of
+//   The gather table is cut into windows of
 //   `win_rows` rows; owners are sorted by pair count and packed VB_SEG_OWNERS = 32 to a warp task.
 //   For task t and window w the task's pairs with a gather row inside w form nsteps[t][w]
 //   "super-steps" of 32 records (one per owner slot, 64 bytes); owners with fewer pairs in the
@@ -146,20 +99,30 @@ struct vb_counts {
     uint32_t* snp_dp;
     int grid_cell, grid_snp, grid_elem;
     int64_t bytes;
-    // gather-stream formats (built lazily, independent of n_donor)
-    GatherSet gA;           // cell pass
-    GatherSet gB;           // SNP pass
-    int gather_failed;      // a build attempt failed (message in vb_last_error); rows path is used
     // window-segment formats (vb_seg.cu), index = table kind: 0 FP64 rows of 128 B (16 columns), 1 fixed-point rows
     // of 64 B (16 columns), 2 FP64 rows of 64 B (8 columns, n_donor <= 8)
     SegSet sA[3];           // cell pass
     SegSet sB[3];           // SNP pass
     int seg_failed[3];
+    // why the automatic selector last chose the row kernels for this matrix: 0 it did not, 1 small matrix (the passes
+    // are launch/latency bound either way), 2 building the segment formats failed (message kept in seg_error),
+    // 3 most pairs carry counts > 31 (residual-dominated, e.g. mitochondrial clone data), 4 n_donor > 16
+    int auto_fallback;
+    char seg_error[256];
 };
 
-// vb_gather.cu
-int vb_gather_build(vb_counts* m, cudaStream_t st);      // builds gA and gB once
-void vb_gather_free(vb_counts* m);
+// every extern "C" entry point runs on the handle's device and leaves the caller's current device untouched
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // vb_seg.cu
 int vb_seg_build(vb_counts* m, int prec, cudaStream_t st);   // builds sA[prec] and sB[prec] once
 void vb_seg_free(vb_counts* m);
@@ -190,10 +153,10 @@ struct EmP {
     const double *lidp, *lidp_kl, *lgtp, *lgtp_kl, *s1p, *s2p;
     double *S1, *S2, *Wt, *ll, *ab, *part, *scal, *elbo;
     int* ctrl;
-    // gather path (vb_gather.cu): Wt is then [B, 2V, 16] (rows of 128 bytes, columns replicated 16/KT times),
+    // segment path (vb_seg.cu): Wt is then [B, 2V, RW] (rows of 128 / 64 bytes, columns replicated RW/KT times),
     // RP the same layout of ID_prob [B, C, 16], H the residual sums [B, max(C, 2V), 16]
     int RW;                    // doubles per row of the padded tables (Wt, RP, H): 16, or 8 for the narrow FP64 segment kernels
-    int tiled, KT;             // tiled: 0 row kernels, 1 gather-stream kernels, 2 window-segment kernels (FP64 tables),
+    int tiled, KT;             // tiled: 0 row kernels, 2 window-segment kernels (FP64 tables),
                                //        3 window-segment kernels (32-bit fixed-point tables)
     double *RP, *H;
     uint32_t *Wq, *RPq;        // tiled == 3: fixed-point copies of Wt [B, 2V, 16] and RP [B, C, 16]
@@ -289,16 +252,13 @@ void vb_launch_end(int cls, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1);
         vb_launch_end(cls, st, e0__, e1__);                             \
     } while (0)
 
-// vb_gather.cu
-void vb_gather_geometry(const vb_counts* m, const GatherSet& g, int* grid, int* nwarps);
-int vb_gather_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, double* plain_out,
-                     cudaStream_t st);
+// vb_seg.cu
 int vb_pad_rows_launch(const vb_counts* m, const double* src, int64_t n_row, int K, int KT, int RW, int B, double* dst,
                        cudaStream_t st);
 enum { GM_CELL = 0, GM_CELL_LL = 1, GM_SNP = 2, GM_PLAIN = 3 };
-// vb_seg.cu
 void vb_seg_geometry(const SegSet& g, int* grid, int* nwarps);
-int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, cudaStream_t st);
+struct SegPlain { double* out; int64_t ld; int off, cols; };       // GM_PLAIN: out[owner * ld + off + column], column < cols
+int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, const SegPlain* plain, cudaStream_t st);
 int vb_seg_quantise_rows(const vb_counts* m, const EmP& p, cudaStream_t st);   // RP -> RPq before the first SNP pass
 
 // error plumbing -------------------------------------------------------------------------------

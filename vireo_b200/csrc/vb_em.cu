@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(VB_THREADS) k_theta_ase(const EmP p, const int
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(VB_THREADS) k_theta_sums(const EmP p) {
     const int b = blockIdx.y;
+    if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
     const int K = p.K, G = p.G;
     const int64_t VK = p.V * K;
     const double* __restrict__ GT = p.GT + (size_t)b * VK * G;
@@ -729,7 +730,7 @@ __global__ void __launch_bounds__(VB_THREADS) k_gt(const EmP p, const int do_gt)
                 if (pr[g] > 0.0) kl += pr[g] * (log(pr[g]) - p.lgtp_kl[(size_t)e * G + g]);
             }
         if (p.tiled) {
-            // gather-table rows of 128 bytes, columns replicated 16/KT times (vb_gather.cu)
+            // gather-table rows of RW doubles, columns replicated RW/KT times (vb_seg.cu)
             double* w0 = p.Wt + ((size_t)b * p.V + i) * 2 * p.RW;
             for (int c = k; c < p.RW; c += p.KT) { w0[c] = wb; w0[p.RW + c] = wa; }
             if (p.tiled == 3) {
@@ -824,7 +825,8 @@ __global__ void __launch_bounds__(VB_THREADS) k_log_prior(const double* __restri
 // ---------------------------------------------------------------------------------------------
 // k_elbo: final sums + the convergence rule.  advance = 1 inside the fit loop.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_elbo(const EmP p, const int advance) {
+// cell_terms != nullptr (cell-sharded fit): {LB_p, KL_ID} already summed over the blocks and over the ranks
+__global__ void __launch_bounds__(128) k_elbo(const EmP p, const int advance, const double* __restrict__ cell_terms) {
     const int b = blockIdx.y;
     int* ctrl = p.ctrl + b * VB_CTRL_N;
     if (advance && ctrl[0]) return;
@@ -832,8 +834,8 @@ __global__ void __launch_bounds__(128) k_elbo(const EmP p, const int advance) {
     const double* part = p.part + (size_t)b * p.part_stride;
     __shared__ double tot[4];
     double t = 0.0;
-    if (w == 0) for (int i = lane; i < p.n_cellblk; i += 32) t += part[p.off_cell + 2 * i];
-    else if (w == 1) for (int i = lane; i < p.n_cellblk; i += 32) t += part[p.off_cell + 2 * i + 1];
+    if (w == 0) { if (cell_terms) { if (lane == 0) t = cell_terms[0]; } else for (int i = lane; i < p.n_cellblk; i += 32) t += part[p.off_cell + 2 * i]; }
+    else if (w == 1) { if (cell_terms) { if (lane == 0) t = cell_terms[1]; } else for (int i = lane; i < p.n_cellblk; i += 32) t += part[p.off_cell + 2 * i + 1]; }
     else if (w == 2) { if (!p.bmm) for (int i = lane; i < p.n_elemblk; i += 32) t += part[p.off_klgt + i]; }
     else for (int i = lane; i < p.n_klth; i += 32) t += part[p.off_klth + i];
     t = warp_sum(t);
@@ -859,6 +861,18 @@ __global__ void __launch_bounds__(128) k_elbo(const EmP p, const int advance) {
     ctrl[2] = it;                                                // the reference returns ELBO[:it]
     if (brk || it + 1 >= p.max_iter) ctrl[0] = 1;
     else ctrl[1] = it + 1;
+}
+
+// cell-sharded fit: the block partials {LB_p, KL_ID} of the local cell pass -> two doubles behind S1 | S2 in the
+// exchange buffer (summed over the ranks by the next iteration's all-reduce)
+__global__ void __launch_bounds__(64) k_xchg_pack(const EmP p, double* __restrict__ out2) {
+    if (p.ctrl && p.ctrl[0]) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const double* part = p.part;
+    double t = 0.0;
+    for (int i = lane; i < p.n_cellblk; i += 32) t += part[p.off_cell + 2 * i + w];
+    t = warp_sum(t);
+    if (lane == 0) out2[w] = t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -896,14 +910,22 @@ __global__ void __launch_bounds__(64) k_doublet_theta(const double* __restrict__
     }
 }
 
+// cw == 0: Wt[V][2][K2] (row kernels).  cw = 16 / 8: column chunks of cw as gather tables of the segment kernels,
+// Wt[chunk][2V][cw], columns past K2 zero.
 __global__ void __launch_bounds__(VB_THREADS) k_doublet_tables(const double* __restrict__ GT, const double* __restrict__ ab2,
-                                                               int64_t V, int K, int G, int ase,
+                                                               int64_t V, int K, int G, int ase, int cw,
                                                                double* __restrict__ Wt) {
     const int G2 = G + G * (G - 1) / 2;
     const int K2 = K + K * (K - 1) / 2;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < V * K2; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = e / K2;
-        const int c = (int)(e % K2);
+    const int KP = cw ? (K2 + cw - 1) / cw * cw : K2;        // columns incl. padding
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < V * KP; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / KP;
+        const int c = (int)(e % KP);
+        if (c >= K2) {
+            const size_t o = ((size_t)(c / cw) * 2 * V + 2 * i) * cw + c % cw;
+            Wt[o] = 0.0; Wt[o + cw] = 0.0;
+            continue;
+        }
         const double* ab = ab2 + (size_t)(ase ? i : 0) * 2 * G2;
         const double* gi = GT + (size_t)i * K * G;
         double wa = 0.0, wb = 0.0;
@@ -922,8 +944,13 @@ __global__ void __launch_bounds__(VB_THREADS) k_doublet_tables(const double* __r
                 for (int g2 = g1 + 1; g2 < G; ++g2) { pr[cc] = A[g1] * Bq[g2] + A[g2] * Bq[g1]; z += pr[cc]; ++cc; }   // :128-131
             for (int g = 0; g < G2; ++g) { const double pg = pr[g] / z; wa += pg * ab[g]; wb += pg * ab[G2 + g]; }   // :133
         }
-        Wt[(size_t)i * 2 * K2 + c] = wb;
-        Wt[(size_t)i * 2 * K2 + K2 + c] = wa;
+        if (cw) {
+            const size_t o = ((size_t)(c / cw) * 2 * V + 2 * i) * cw + c % cw;
+            Wt[o] = wb; Wt[o + cw] = wa;
+        } else {
+            Wt[(size_t)i * 2 * K2 + c] = wb;
+            Wt[(size_t)i * 2 * K2 + K2 + c] = wa;
+        }
     }
 }
 
@@ -955,6 +982,7 @@ __global__ void __launch_bounds__(VB_THREADS) k_doublet_softmax(const double* __
         if (lane == 0) llr[j] = md - ms;
     }
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // host side: dispatch, iteration driver, C ABI
@@ -1004,8 +1032,7 @@ static bool rows_lane_ok(int K, int64_t nnz, int64_t n_row) {
 }
 
 static int launch_cell(const vb_counts* m, const EmP& p, int mode, cudaStream_t st) {
-    if (p.tiled >= 2) return vb_seg_launch(m, p, 0, mode == 0 ? GM_CELL : GM_CELL_LL, 0, st);
-    if (p.tiled) return vb_gather_launch(m, p, 0, mode == 0 ? GM_CELL : GM_CELL_LL, 0, nullptr, st);
+    if (p.tiled >= 2) return vb_seg_launch(m, p, 0, mode == 0 ? GM_CELL : GM_CELL_LL, 0, nullptr, st);
     int KT, KR;
     if (!tile_for(p.K, KT, KR)) { vb_set_error("n_donor=%d outside [1, %d]", p.K, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
     const CountsView v = view_of(m);
@@ -1024,8 +1051,7 @@ static int launch_cell(const vb_counts* m, const EmP& p, int mode, cudaStream_t 
 }
 
 static int launch_snp(const vb_counts* m, const EmP& p, int theta_mode, cudaStream_t st) {
-    if (p.tiled >= 2) return vb_seg_launch(m, p, 1, GM_SNP, theta_mode, st);
-    if (p.tiled) return vb_gather_launch(m, p, 1, GM_SNP, theta_mode, nullptr, st);
+    if (p.tiled >= 2) return vb_seg_launch(m, p, 1, GM_SNP, theta_mode, nullptr, st);
     int KT, KR;
     if (!tile_for(p.K, KT, KR)) { vb_set_error("n_donor=%d outside [1, %d]", p.K, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
     const CountsView v = view_of(m);
@@ -1044,15 +1070,16 @@ static int launch_snp(const vb_counts* m, const EmP& p, int theta_mode, cudaStre
 }
 
 // ---------------------------------------------------------------------------------------------
-// path selection: rows (v1, one warp per row, L2 gathers) or gather (vb_gather.cu, ring-slab streams)
+// kernel family of the two sparse passes: row kernels (one warp per row, L2 gathers) or the window-segment
+// kernels of vb_seg.cu (table windows in shared memory)
 // ---------------------------------------------------------------------------------------------
-static int g_path = 0;                       // 0 auto, 1 rows, 2 gather streams, 3 segments (FP64 tables), 4 segments (fixed-point tables)
-#define VB_GATHER_MIN_NNZ (4ll << 20)        // below this the passes are launch/latency bound either way
+static int g_path = 0;                       // 0 auto, 1 rows, 3 segments (FP64 tables), 4 segments (fixed-point tables)
+static int g_graphs = 1;
+#define VB_SEG_MIN_NNZ (4ll << 20)           // below this the passes are launch/latency bound either way
 
-extern "C" void vb_set_path(int mode) { g_path = mode < 0 || mode > 4 ? 0 : mode; }
+extern "C" void vb_set_path(int mode) { g_path = (mode == 1 || mode == 3 || mode == 4) ? mode : 0; }
+extern "C" void vb_set_graphs(int on) { g_graphs = on != 0; }
 
-// *use = kernel family serving this (counts, K): 0 rows, 1 gather streams, 2 window segments with FP64 tables,
-// 3 window segments with fixed-point tables (`fixed_ok`: the caller can build them); builds the formats on first use
 static int kt_for(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : 16); }
 
 // narrow FP64 rows (8 doubles = 64 bytes) serve n_donor <= 8; VIREO_B200_SEG_NARROW=0 keeps the 16-column rows
@@ -1061,59 +1088,66 @@ static bool seg_narrow_ok(int K) {
     return on && kt_for(K) <= 8;
 }
 
-static int want_gather(const vb_counts* mc, int K, int fixed_ok, int* use) {
+// *use = kernel family serving this (counts, K): 0 rows, 2 window segments with FP64 tables, 3 window segments with
+// fixed-point tables (`fixed_ok`: the caller can build them).  Formats are built on first use, on `st`.
+static int select_family(const vb_counts* mc, int K, int fixed_ok, cudaStream_t st, int* use) {
     vb_counts* m = const_cast<vb_counts*>(mc);
     *use = 0;
-    if (g_path == 1 || K > VB_ROW_DOUBLES) return VB_OK;
+    if (g_path == 1) return VB_OK;
+    if (K > VB_ROW_DOUBLES) { if (g_path == 0) m->auto_fallback = 4; return VB_OK; }
     const int fp64_fmt = seg_narrow_ok(K) ? 2 : 0;      // FP64 tables: 64-byte rows when 8 columns are enough
     if (g_path == 3 || g_path == 4) {
         int prec = (g_path == 4 && fixed_ok) ? 1 : fp64_fmt;
-        int rc = vb_seg_build(m, prec, 0);
+        int rc = vb_seg_build(m, prec, st);
         if (rc) return rc;
         // the fixed-point kernel keeps odd slots scaled by 2^16: one owner's stream may carry fewer than 2^16 reads
         if (prec == 1 && (m->sA[1].max_reads >= 65536 || m->sB[1].max_reads >= 65536)) {
             prec = fp64_fmt;
-            if ((rc = vb_seg_build(m, prec, 0))) return rc;
+            if ((rc = vb_seg_build(m, prec, st))) return rc;
         }
         *use = prec == 1 ? 3 : 2;
         return VB_OK;
     }
-    if (g_path == 0) {
-        // automatic: the window-segment kernels with FP64 tables for large count matrices; row kernels when the
-        // passes are launch/latency bound anyway, or when most pairs carry large counts (e.g. mitochondrial clone
-        // data) and the residual kernel would do all the work
-        if (m->N < VB_GATHER_MIN_NNZ || m->seg_failed[fp64_fmt]) return VB_OK;
-        if (vb_seg_build(m, fp64_fmt, 0)) return VB_OK;
-        const int64_t pairs = m->sA[fp64_fmt].n_light + m->sA[fp64_fmt].n_heavy;
-        if (m->sA[fp64_fmt].n_heavy * 4 > pairs) return VB_OK;
-        *use = 2;
+    // automatic: the window-segment kernels with FP64 tables for large count matrices; row kernels when the passes
+    // are launch/latency bound anyway, or when most pairs carry large counts (e.g. mitochondrial clone data) and the
+    // residual kernel would do all the work.  A FAILED format build is remembered with its message (vb_counts_info
+    // 60 / vb_counts_note): the row kernels then serve the matrix, several times slower, and the caller can tell.
+    if (m->N < VB_SEG_MIN_NNZ) { m->auto_fallback = 1; return VB_OK; }
+    if (m->seg_failed[fp64_fmt]) { m->auto_fallback = 2; return VB_OK; }
+    if (vb_seg_build(m, fp64_fmt, st)) {
+        m->auto_fallback = 2;
+        snprintf(m->seg_error, sizeof(m->seg_error), "%s", vb_last_error());
         return VB_OK;
     }
-    const int rc = vb_gather_build(m, 0);      // g_path == 2
-    if (rc) return rc;
-    *use = 1;
+    const int64_t pairs = m->sA[fp64_fmt].n_light + m->sA[fp64_fmt].n_heavy;
+    if (m->sA[fp64_fmt].n_heavy * 4 > pairs) { m->auto_fallback = 3; return VB_OK; }
+    m->auto_fallback = 0;
+    *use = 2;
     return VB_OK;
 }
 
+// Block-partial layout.  The capacities cover EVERY kernel family whatever formats happen to be built, so a `part`
+// workspace sized once stays valid when another family serves a later call.
+static int seg_grid_cap(int64_t n_owner, int sm) {
+    const int64_t tasks = (n_owner + VB_SEG_OWNERS - 1) / VB_SEG_OWNERS;
+    int64_t cap = (tasks + VB_SEG_MAX_WARPS - 1) / VB_SEG_MAX_WARPS;
+    if (cap < sm) cap = sm;
+    return (int)cap + 1;
+}
+
 static void part_layout(const vb_counts* m, EmP& p) {
-    int ga = 0, gb = 0, nw;
-    int cap_snp = m->grid_snp > m->grid_elem ? m->grid_snp : m->grid_elem, cap_cell = m->grid_cell;
-    if (m->gA.built) {
-        vb_gather_geometry(m, m->gA, &ga, &nw); vb_gather_geometry(m, m->gB, &gb, &nw);
-        if (ga > cap_cell) cap_cell = ga;
-        if (gb > cap_snp) cap_snp = gb;
+    int cap_snp = m->grid_snp > m->grid_elem ? m->grid_snp : m->grid_elem, cap_cell = m->grid_cell, nw;
+    const int sc = seg_grid_cap(m->C, m->sm_count), ss = seg_grid_cap(2 * m->V, m->sm_count);
+    if (sc > cap_cell) cap_cell = sc;
+    if (ss > cap_snp) cap_snp = ss;
+    int sa = 0, sb = 0;
+    if (p.tiled >= 2) {
+        const int fmt = p.tiled == 3 ? 1 : (p.RW == 8 ? 2 : 0);
+        vb_seg_geometry(m->sA[fmt], &sa, &nw); vb_seg_geometry(m->sB[fmt], &sb, &nw);
     }
-    int sa[3] = {0, 0, 0}, sb[3] = {0, 0, 0};
-    for (int q = 0; q < 3; ++q)
-        if (m->sA[q].built && m->sB[q].built) {
-            vb_seg_geometry(m->sA[q], &sa[q], &nw); vb_seg_geometry(m->sB[q], &sb[q], &nw);
-            if (sa[q] > cap_cell) cap_cell = sa[q];
-            if (sb[q] > cap_snp) cap_snp = sb[q];
-        }
-    const int fmt = p.tiled == 3 ? 1 : (p.RW == 8 ? 2 : 0);
-    p.n_snpblk = p.tiled >= 2 ? sb[fmt] : (p.tiled ? gb : m->grid_snp);
+    p.n_snpblk = p.tiled >= 2 ? sb : m->grid_snp;
     p.n_elemblk = m->grid_elem;
-    p.n_cellblk = p.tiled >= 2 ? sa[fmt] : (p.tiled ? ga : m->grid_cell);
+    p.n_cellblk = p.tiled >= 2 ? sa : m->grid_cell;
     p.n_klth = (p.bmm || p.ase) ? m->grid_elem : 1;
     p.off_theta = 0;
     p.off_klgt = p.off_theta + cap_snp * 2 * VB_MAX_GT;
@@ -1122,88 +1156,11 @@ static void part_layout(const vb_counts* m, EmP& p) {
     p.part_stride = p.off_klth + m->grid_elem;
 }
 
-static int fill_vireo(const vb_counts* m, const vb_vireo_args* a, EmP& p) {
-    if (!m || !a) { vb_set_error("NULL argument"); return VB_E_ARG; }
-    if (a->n_gt < 1 || a->n_gt > VB_MAX_GT) { vb_set_error("n_GT=%d outside [1, %d]", a->n_gt, VB_MAX_GT); return VB_E_UNSUPPORTED; }
-    if (a->n_donor < 1 || a->n_donor > VB_MAX_DONOR) { vb_set_error("n_donor=%d outside [1, %d]", a->n_donor, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
-    if (a->n_batch < 1 || a->n_batch > 65535) { vb_set_error("n_batch=%d outside [1, 65535]", a->n_batch); return VB_E_ARG; }
-    memset(&p, 0, sizeof(p));
-    p.C = m->C; p.V = m->V; p.T = a->ase_mode ? m->V : 1;
-    p.K = a->n_donor; p.G = a->n_gt; p.B = a->n_batch; p.bmm = 0;
-    p.ase = a->ase_mode; p.learn_gt = a->learn_gt; p.learn_theta = a->learn_theta; p.fix_beta_sum = a->fix_beta_sum;
-    p.id_rows = a->id_prior_rows; p.thp_rows = a->theta_prior_rows;
-    p.max_iter = a->max_iter; p.min_iter = a->min_iter; p.delay = a->delay_fit_theta; p.eps = a->epsilon_conv;
-    p.R = a->id_prob; p.GT = a->gt_prob; p.mu = a->beta_mu; p.sum = a->beta_sum;
-    p.lidp = a->log_id_prior; p.lidp_kl = a->log_id_prior_kl; p.lgtp = a->log_gt_prior; p.lgtp_kl = a->log_gt_prior_kl;
-    p.s1p = a->s1_prior; p.s2p = a->s2_prior;
-    p.S1 = a->S1; p.S2 = a->S2; p.Wt = a->W; p.ll = a->loglik; p.ab = a->ab; p.part = a->part;
-    p.scal = a->scal; p.elbo = a->elbo; p.ctrl = a->ctrl;
-    if (!p.R || !p.GT || !p.mu || !p.sum || !p.lidp || !p.lidp_kl || !p.lgtp || !p.lgtp_kl || !p.s1p || !p.s2p || !p.S1 ||
-        !p.S2 || !p.Wt || !p.ll || !p.ab || !p.part || !p.scal || !p.ctrl) {
-        vb_set_error("NULL device pointer in vb_vireo_args");
-        return VB_E_ARG;
-    }
-    {
-        int use = 0;
-        const int rc = want_gather(m, p.K, !p.ase, &use);
-        if (rc) return rc;
-        p.tiled = use; p.KT = kt_for(p.K); p.RP = a->rpad; p.H = a->heavy;
-        p.RW = (use == 2 && seg_narrow_ok(p.K)) ? 8 : VB_ROW_DOUBLES;
-        if (use && (!p.RP || !p.H)) { vb_set_error("rpad / heavy workspace is NULL (see vb_vireo_ws_sizes)"); return VB_E_ARG; }
-        if (use == 3) {   // fixed-point copies live behind the FP64 tables of the same workspaces
-            p.Wq = reinterpret_cast<uint32_t*>(p.Wt + (size_t)p.B * p.V * 2 * VB_ROW_DOUBLES);
-            p.RPq = reinterpret_cast<uint32_t*>(p.RP + (size_t)p.B * p.C * VB_ROW_DOUBLES);
-            p.qscale = p.ab + (size_t)p.B * p.T * 2 * p.G;
-        }
-    }
-    if ((p.id_rows != 1 && p.id_rows != m->C) || (p.thp_rows != 1 && p.thp_rows != p.T)) {
-        vb_set_error("prior rows must be 1 or the full extent");
-        return VB_E_ARG;
-    }
-    part_layout(m, p);
-    return VB_OK;
-}
-
-static int fill_bmm(const vb_counts* m, const vb_bmm_args* a, EmP& p) {
-    if (!m || !a) { vb_set_error("NULL argument"); return VB_E_ARG; }
-    if (a->n_donor < 1 || a->n_donor > VB_MAX_DONOR) { vb_set_error("n_donor=%d outside [1, %d]", a->n_donor, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
-    if (a->n_batch < 1 || a->n_batch > 65535) { vb_set_error("n_batch=%d outside [1, 65535]", a->n_batch); return VB_E_ARG; }
-    memset(&p, 0, sizeof(p));
-    p.C = m->C; p.V = m->V; p.T = m->V;
-    p.K = a->n_donor; p.G = 1; p.B = a->n_batch; p.bmm = 1;
-    p.fix_beta_sum = a->fix_beta_sum; p.learn_theta = 1;
-    p.id_rows = a->id_prior_rows; p.thp_rows = (int)m->V;
-    p.max_iter = a->max_iter; p.min_iter = a->min_iter; p.eps = a->epsilon_conv;
-    p.R = a->id_prob; p.mu = a->beta_mu; p.sum = a->beta_sum;
-    p.lidp = a->log_id_prior; p.lidp_kl = a->log_id_prior_kl; p.s1p = a->s1_prior; p.s2p = a->s2_prior;
-    p.S1 = a->S1; p.S2 = a->S2; p.Wt = a->W; p.ll = a->loglik; p.part = a->part;
-    p.scal = a->scal; p.elbo = a->elbo; p.ctrl = a->ctrl;
-    if (!p.R || !p.mu || !p.sum || !p.lidp || !p.lidp_kl || !p.s1p || !p.s2p || !p.S1 || !p.S2 || !p.Wt ||
-        !p.ll || !p.part || !p.scal || !p.ctrl) {
-        vb_set_error("NULL device pointer in vb_bmm_args");
-        return VB_E_ARG;
-    }
-    {
-        int use = 0;
-        const int rc = want_gather(m, p.K, 0, &use);
-        if (rc) return rc;
-        p.tiled = use; p.KT = kt_for(p.K); p.RP = a->rpad; p.H = a->heavy;
-        p.RW = (use == 2 && seg_narrow_ok(p.K)) ? 8 : VB_ROW_DOUBLES;
-        if (use && (!p.RP || !p.H)) { vb_set_error("rpad / heavy workspace is NULL (see vb_bmm_ws_sizes)"); return VB_E_ARG; }
-    }
-    if (p.id_rows != 1 && p.id_rows != m->C) { vb_set_error("id_prior_rows must be 1 or n_cell"); return VB_E_ARG; }
-    part_layout(m, p);
-    return VB_OK;
-}
-
-static int ws_sizes(const vb_counts* m, int K, int G, int B, int T_is_V, vb_ws_sizes* out) {
-    if (!m || !out || K < 1 || B < 1) { vb_set_error("bad argument"); return VB_E_ARG; }
+// workspace element counts of the family `use`
+static void ws_for(const vb_counts* m, int K, int G, int B, int T_is_V, int use, vb_ws_sizes* out) {
     EmP p;
     memset(&p, 0, sizeof(p));
     p.bmm = G == 0; p.ase = T_is_V;
-    int use = 0;
-    const int rc = want_gather(m, K, G != 0 && !T_is_V, &use);
-    if (rc) return rc;
     p.tiled = use;
     p.RW = (use == 2 && seg_narrow_ok(K)) ? 8 : VB_ROW_DOUBLES;
     part_layout(m, p);
@@ -1222,15 +1179,117 @@ static int ws_sizes(const vb_counts* m, int K, int G, int B, int T_is_V, vb_ws_s
     out->part = (int64_t)B * p.part_stride;
     out->scal = (int64_t)B * VB_SCAL_N;
     out->ctrl = (int64_t)B * VB_CTRL_N;
+}
+
+static int ws_check(const vb_ws_sizes& need, const vb_ws_sizes& have, bool s_external) {
+    const bool ok = (s_external || have.S >= need.S) && have.W >= need.W && have.loglik >= need.loglik && have.ab >= need.ab &&
+                    have.part >= need.part && have.scal >= need.scal && have.ctrl >= need.ctrl && have.rpad >= need.rpad &&
+                    have.heavy >= need.heavy;
+    if (!ok) {
+        vb_set_error("workspaces do not fit the kernel family in use (need S %lld W %lld loglik %lld ab %lld part %lld rpad %lld "
+                     "heavy %lld; have S %lld W %lld loglik %lld ab %lld part %lld rpad %lld heavy %lld): size them with "
+                     "vb_*_ws_sizes AFTER the last vb_set_path and pass the sizes in args.ws",
+                     (long long)need.S, (long long)need.W, (long long)need.loglik, (long long)need.ab, (long long)need.part,
+                     (long long)need.rpad, (long long)need.heavy, (long long)have.S, (long long)have.W, (long long)have.loglik,
+                     (long long)have.ab, (long long)have.part, (long long)have.rpad, (long long)have.heavy);
+        return VB_E_ARG;
+    }
     return VB_OK;
 }
 
-extern "C" int vb_vireo_ws_sizes(const vb_counts* m, int n_donor, int n_gt, int n_batch, int ase_mode, vb_ws_sizes* out) {
-    if (n_gt < 1) { vb_set_error("n_GT must be >= 1"); return VB_E_ARG; }
-    return ws_sizes(m, n_donor, n_gt, n_batch, ase_mode, out);
+static int fill_vireo(const vb_counts* m, const vb_vireo_args* a, EmP& p, cudaStream_t st, bool s_external = false) {
+    if (!m || !a) { vb_set_error("NULL argument"); return VB_E_ARG; }
+    if (a->n_gt < 1 || a->n_gt > VB_MAX_GT) { vb_set_error("n_GT=%d outside [1, %d]", a->n_gt, VB_MAX_GT); return VB_E_UNSUPPORTED; }
+    if (a->n_donor < 1 || a->n_donor > VB_MAX_DONOR) { vb_set_error("n_donor=%d outside [1, %d]", a->n_donor, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
+    if (a->n_batch < 1 || a->n_batch > 65535) { vb_set_error("n_batch=%d outside [1, 65535]", a->n_batch); return VB_E_ARG; }
+    memset(&p, 0, sizeof(p));
+    p.C = m->C; p.V = m->V; p.T = a->ase_mode ? m->V : 1;
+    p.K = a->n_donor; p.G = a->n_gt; p.B = a->n_batch; p.bmm = 0;
+    p.ase = a->ase_mode; p.learn_gt = a->learn_gt; p.learn_theta = a->learn_theta; p.fix_beta_sum = a->fix_beta_sum;
+    p.id_rows = a->id_prior_rows; p.thp_rows = a->theta_prior_rows;
+    p.max_iter = a->max_iter; p.min_iter = a->min_iter; p.delay = a->delay_fit_theta; p.eps = a->epsilon_conv;
+    p.R = a->id_prob; p.GT = a->gt_prob; p.mu = a->beta_mu; p.sum = a->beta_sum;
+    p.lidp = a->log_id_prior; p.lidp_kl = a->log_id_prior_kl; p.lgtp = a->log_gt_prior; p.lgtp_kl = a->log_gt_prior_kl;
+    p.s1p = a->s1_prior; p.s2p = a->s2_prior;
+    p.S1 = a->S1; p.S2 = a->S2; p.Wt = a->W; p.ll = a->loglik; p.ab = a->ab; p.part = a->part;
+    p.scal = a->scal; p.elbo = a->elbo; p.ctrl = a->ctrl;
+    if (!p.R || !p.GT || !p.mu || !p.sum || !p.lidp || !p.lidp_kl || !p.lgtp || !p.lgtp_kl || !p.s1p || !p.s2p ||
+        (!s_external && (!p.S1 || !p.S2)) || !p.Wt || !p.ll || !p.ab || !p.part || !p.scal || !p.ctrl) {
+        vb_set_error("NULL device pointer in vb_vireo_args");
+        return VB_E_ARG;
+    }
+    int use = 0;
+    const int rc = select_family(m, p.K, !p.ase, st, &use);
+    if (rc) return rc;
+    p.tiled = use; p.KT = kt_for(p.K); p.RP = a->rpad; p.H = a->heavy;
+    p.RW = (use == 2 && seg_narrow_ok(p.K)) ? 8 : VB_ROW_DOUBLES;
+    if (use && (!p.RP || !p.H)) { vb_set_error("rpad / heavy workspace is NULL (see vb_vireo_ws_sizes)"); return VB_E_ARG; }
+    if (use == 3) {   // fixed-point copies live behind the FP64 tables of the same workspaces
+        p.Wq = reinterpret_cast<uint32_t*>(p.Wt + (size_t)p.B * p.V * 2 * VB_ROW_DOUBLES);
+        p.RPq = reinterpret_cast<uint32_t*>(p.RP + (size_t)p.B * p.C * VB_ROW_DOUBLES);
+        p.qscale = p.ab + (size_t)p.B * p.T * 2 * p.G;
+    }
+    if ((p.id_rows != 1 && p.id_rows != m->C) || (p.thp_rows != 1 && p.thp_rows != p.T)) {
+        vb_set_error("prior rows must be 1 or the full extent");
+        return VB_E_ARG;
+    }
+    vb_ws_sizes need;
+    ws_for(m, p.K, p.G, p.B, p.ase, use, &need);
+    if (ws_check(need, a->ws, s_external)) return VB_E_ARG;
+    part_layout(m, p);
+    return VB_OK;
 }
-extern "C" int vb_bmm_ws_sizes(const vb_counts* m, int n_donor, int n_batch, vb_ws_sizes* out) {
-    return ws_sizes(m, n_donor, 0, n_batch, 1, out);
+
+static int fill_bmm(const vb_counts* m, const vb_bmm_args* a, EmP& p, cudaStream_t st) {
+    if (!m || !a) { vb_set_error("NULL argument"); return VB_E_ARG; }
+    if (a->n_donor < 1 || a->n_donor > VB_MAX_DONOR) { vb_set_error("n_donor=%d outside [1, %d]", a->n_donor, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
+    if (a->n_batch < 1 || a->n_batch > 65535) { vb_set_error("n_batch=%d outside [1, 65535]", a->n_batch); return VB_E_ARG; }
+    memset(&p, 0, sizeof(p));
+    p.C = m->C; p.V = m->V; p.T = m->V;
+    p.K = a->n_donor; p.G = 1; p.B = a->n_batch; p.bmm = 1;
+    p.fix_beta_sum = a->fix_beta_sum; p.learn_theta = 1;
+    p.id_rows = a->id_prior_rows; p.thp_rows = (int)m->V;
+    p.max_iter = a->max_iter; p.min_iter = a->min_iter; p.eps = a->epsilon_conv;
+    p.R = a->id_prob; p.mu = a->beta_mu; p.sum = a->beta_sum;
+    p.lidp = a->log_id_prior; p.lidp_kl = a->log_id_prior_kl; p.s1p = a->s1_prior; p.s2p = a->s2_prior;
+    p.S1 = a->S1; p.S2 = a->S2; p.Wt = a->W; p.ll = a->loglik; p.part = a->part;
+    p.scal = a->scal; p.elbo = a->elbo; p.ctrl = a->ctrl;
+    if (!p.R || !p.mu || !p.sum || !p.lidp || !p.lidp_kl || !p.s1p || !p.s2p || !p.S1 || !p.S2 || !p.Wt ||
+        !p.ll || !p.part || !p.scal || !p.ctrl) {
+        vb_set_error("NULL device pointer in vb_bmm_args");
+        return VB_E_ARG;
+    }
+    int use = 0;
+    const int rc = select_family(m, p.K, 0, st, &use);
+    if (rc) return rc;
+    p.tiled = use; p.KT = kt_for(p.K); p.RP = a->rpad; p.H = a->heavy;
+    p.RW = (use == 2 && seg_narrow_ok(p.K)) ? 8 : VB_ROW_DOUBLES;
+    if (use && (!p.RP || !p.H)) { vb_set_error("rpad / heavy workspace is NULL (see vb_bmm_ws_sizes)"); return VB_E_ARG; }
+    if (p.id_rows != 1 && p.id_rows != m->C) { vb_set_error("id_prior_rows must be 1 or n_cell"); return VB_E_ARG; }
+    vb_ws_sizes need;
+    ws_for(m, p.K, 0, p.B, 1, use, &need);
+    if (ws_check(need, a->ws, false)) return VB_E_ARG;
+    part_layout(m, p);
+    return VB_OK;
+}
+
+static int ws_sizes(const vb_counts* m, int K, int G, int B, int T_is_V, cudaStream_t st, vb_ws_sizes* out) {
+    if (!m || !out || K < 1 || B < 1) { vb_set_error("bad argument"); return VB_E_ARG; }
+    DeviceGuard dg(m->device);
+    int use = 0;
+    const int rc = select_family(m, K, G != 0 && !T_is_V, st, &use);
+    if (rc) return rc;
+    ws_for(m, K, G, B, T_is_V, use, out);
+    return VB_OK;
+}
+
+extern "C" int vb_vireo_ws_sizes(const vb_counts* m, int n_donor, int n_gt, int n_batch, int ase_mode, void* stream,
+                                 vb_ws_sizes* out) {
+    if (n_gt < 1) { vb_set_error("n_GT must be >= 1"); return VB_E_ARG; }
+    return ws_sizes(m, n_donor, n_gt, n_batch, ase_mode, (cudaStream_t)stream, out);
+}
+extern "C" int vb_bmm_ws_sizes(const vb_counts* m, int n_donor, int n_batch, void* stream, vb_ws_sizes* out) {
+    return ws_sizes(m, n_donor, 0, n_batch, 1, (cudaStream_t)stream, out);
 }
 
 // one Vireo iteration; theta_mode / gt flag as documented on the kernels
@@ -1257,7 +1316,7 @@ static int vireo_iteration(const vb_counts* m, const EmP& p, int phases, bool in
     if (phases & VB_PH_ID) { if ((rc = launch_cell(m, p, 0, st))) return rc; }
     else if (phases & VB_PH_LOGLIK) { if ((rc = launch_cell(m, p, 1, st))) return rc; }
     else if (phases & VB_PH_ELBO) { VB_LAUNCH(6, st, k_terms<<<dim3(p.n_cellblk, p.B), VB_THREADS, 0, st>>>(p)); VB_CUDA(cudaGetLastError()); }
-    if (phases & VB_PH_ELBO) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, in_loop ? 1 : 0)); VB_CUDA(cudaGetLastError()); }
+    if (phases & VB_PH_ELBO) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, in_loop ? 1 : 0, nullptr)); VB_CUDA(cudaGetLastError()); }
     return VB_OK;
 }
 
@@ -1271,7 +1330,7 @@ static int bmm_iteration(const vb_counts* m, const EmP& p, int phases, bool in_l
     if (phases & VB_PH_ID) { if ((rc = launch_cell(m, p, 0, st))) return rc; }
     else if (phases & VB_PH_LOGLIK) { if ((rc = launch_cell(m, p, 1, st))) return rc; }
     else if (phases & VB_PH_ELBO) { VB_LAUNCH(6, st, k_terms<<<dim3(p.n_cellblk, p.B), VB_THREADS, 0, st>>>(p)); VB_CUDA(cudaGetLastError()); }
-    if (phases & VB_PH_ELBO) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, in_loop ? 1 : 0)); VB_CUDA(cudaGetLastError()); }
+    if (phases & VB_PH_ELBO) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, in_loop ? 1 : 0, nullptr)); VB_CUDA(cudaGetLastError()); }
     return VB_OK;
 }
 
@@ -1279,32 +1338,130 @@ static int bmm_iteration(const vb_counts* m, const EmP& p, int phases, bool in_l
 static thread_local int32_t* g_pin = nullptr;
 static thread_local int g_pin_n = 0;
 
-static int run_loop(const vb_counts* m, const EmP& p, int poll_every, cudaStream_t st) {
-    if (p.max_iter < 1) { vb_set_error("max_iter must be >= 1"); return VB_E_ARG; }
-    if (!p.elbo) { vb_set_error("elbo output is NULL"); return VB_E_ARG; }
-    const int n_ctrl = p.B * VB_CTRL_N;
+static int pin_for(int n_ctrl) {
     if (g_pin_n < n_ctrl) {
         if (g_pin) cudaFreeHost(g_pin);
         g_pin = nullptr; g_pin_n = 0;
         VB_CUDA(cudaMallocHost(&g_pin, n_ctrl * sizeof(int32_t)));
         g_pin_n = n_ctrl;
     }
+    return VB_OK;
+}
+
+static int all_done(const EmP& p, cudaStream_t st, bool* done) {
+    const int n_ctrl = p.B * VB_CTRL_N;
+    VB_CUDA(cudaMemcpyAsync(g_pin, p.ctrl, n_ctrl * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    VB_CUDA(cudaStreamSynchronize(st));
+    *done = true;
+    for (int b = 0; b < p.B; ++b) *done = *done && g_pin[b * VB_CTRL_N];
+    return VB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Captured iterations.  The kernels of an iteration read the loop state (done flag, iteration counter) from the
+// device, so every iteration of a fit is the SAME sequence of launches with the SAME arguments: a group of n
+// iterations is captured once into a CUDA graph and replayed.  Worth it where an iteration is launch-bound, i.e.
+// on the row-kernel path (small matrices: 5 launches of 5-30 us each); graphs are cached per thread, keyed by every
+// launch argument (EmP, the staged arrays, the launch geometry, n).
+// ---------------------------------------------------------------------------------------------
+struct GraphKey {
+    EmP p;
+    CountsView v;
+    int grid_cell, grid_snp, grid_elem, n_iter, device;
+};
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;
+    int64_t launches[8];
+    uint64_t stamp;
+};
+#define VB_GRAPH_SLOTS 8
+static thread_local GraphEntry g_graphs_cache[VB_GRAPH_SLOTS];
+static thread_local int g_graphs_n = 0;
+static thread_local uint64_t g_graph_stamp = 0;
+static thread_local cudaStream_t g_cap_stream[64] = {nullptr};
+
+static int graph_for(const vb_counts* m, const EmP& p, int n_iter, GraphEntry** out) {
+    GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.p = p; key.v = view_of(m);
+    key.grid_cell = m->grid_cell; key.grid_snp = m->grid_snp; key.grid_elem = m->grid_elem; key.n_iter = n_iter; key.device = m->device;
+    for (int i = 0; i < g_graphs_n; ++i)
+        if (!memcmp(&g_graphs_cache[i].key, &key, sizeof(key))) { g_graphs_cache[i].stamp = ++g_graph_stamp; *out = &g_graphs_cache[i]; return VB_OK; }
+    const int dslot = m->device >= 0 && m->device < 64 ? m->device : 0;
+    if (!g_cap_stream[dslot]) VB_CUDA(cudaStreamCreateWithFlags(&g_cap_stream[dslot], cudaStreamNonBlocking));
+    cudaStream_t cs = g_cap_stream[dslot];
+    int64_t before[8];
+    memcpy(before, g_launches, sizeof(before));
+    VB_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = VB_OK;
+    const int all = VB_PH_SNP | VB_PH_THETA | VB_PH_GT | VB_PH_ID | VB_PH_ELBO;
+    for (int it = 0; it < n_iter && !rc; ++it) rc = p.bmm ? bmm_iteration(m, p, all, true, cs) : vireo_iteration(m, p, all, true, cs);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    int64_t per[8];
+    for (int i = 0; i < 8; ++i) { per[i] = g_launches[i] - before[i]; g_launches[i] = before[i]; }   // counted per replay instead
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) { vb_set_error("stream capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return VB_E_CUDA; }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { vb_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); cudaGetLastError(); return VB_E_CUDA; }
+    int slot = g_graphs_n;
+    if (g_graphs_n < VB_GRAPH_SLOTS) ++g_graphs_n;
+    else {
+        slot = 0;
+        for (int i = 1; i < VB_GRAPH_SLOTS; ++i) if (g_graphs_cache[i].stamp < g_graphs_cache[slot].stamp) slot = i;
+        cudaGraphExecDestroy(g_graphs_cache[slot].exec);
+    }
+    g_graphs_cache[slot].key = key; g_graphs_cache[slot].exec = exec; g_graphs_cache[slot].stamp = ++g_graph_stamp;
+    memcpy(g_graphs_cache[slot].launches, per, sizeof(per));
+    *out = &g_graphs_cache[slot];
+    return VB_OK;
+}
+
+static int run_loop(const vb_counts* m, const EmP& p, int poll_every, cudaStream_t st) {
+    if (p.max_iter < 1) { vb_set_error("max_iter must be >= 1"); return VB_E_ARG; }
+    if (!p.elbo) { vb_set_error("elbo output is NULL"); return VB_E_ARG; }
+    const int n_ctrl = p.B * VB_CTRL_N;
+    int rc = pin_for(n_ctrl);
+    if (rc) return rc;
     VB_CUDA(cudaMemsetAsync(p.ctrl, 0, n_ctrl * sizeof(int32_t), st));
-    if (p.tiled) {   // the SNP pass gathers ID_prob from its 128-byte-row copy
-        int rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.RW, p.B, p.RP, st);
+    if (p.tiled) {   // the SNP pass gathers ID_prob from its padded-row copy
+        rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.RW, p.B, p.RP, st);
         if (!rc && p.tiled == 3) rc = vb_seg_quantise_rows(m, p, st);
         if (rc) return rc;
     }
     if (poll_every <= 0) poll_every = 16;
     const int all = VB_PH_SNP | VB_PH_THETA | VB_PH_GT | VB_PH_ID | VB_PH_ELBO;
+    if (g_graphs && !g_prof_on && p.tiled == 0) {
+        // launch-bound iterations: replay captured groups of up to 16 iterations; the done flags are polled between groups
+        int group = poll_every < 16 ? poll_every : 16;
+        if (group > p.max_iter) group = p.max_iter;
+        int it = 0;
+        bool ok = true;
+        while (it < p.max_iter) {
+            const int n = p.max_iter - it < group ? p.max_iter - it : group;
+            GraphEntry* ge = nullptr;
+            if (graph_for(m, p, n, &ge)) { ok = false; break; }       // capture unavailable: plain launches below
+            VB_CUDA(cudaGraphLaunch(ge->exec, st));
+            for (int i = 0; i < 8; ++i) g_launches[i] += ge->launches[i];
+            it += n;
+            if (it < p.max_iter && it % poll_every == 0) {
+                bool done;
+                if ((rc = all_done(p, st, &done))) return rc;
+                if (done) break;
+            }
+        }
+        if (ok) return VB_OK;
+        if (it > 0) { vb_set_error("graph capture failed mid-fit: %s", vb_last_error()); return VB_E_CUDA; }
+    }
     for (int it = 0; it < p.max_iter; ++it) {
-        const int rc = p.bmm ? bmm_iteration(m, p, all, true, st) : vireo_iteration(m, p, all, true, st);
+        rc = p.bmm ? bmm_iteration(m, p, all, true, st) : vireo_iteration(m, p, all, true, st);
         if (rc) return rc;
         if ((it + 1) % poll_every == 0 && it + 1 < p.max_iter) {
-            VB_CUDA(cudaMemcpyAsync(g_pin, p.ctrl, n_ctrl * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-            VB_CUDA(cudaStreamSynchronize(st));
-            bool done = true;
-            for (int b = 0; b < p.B; ++b) done = done && g_pin[b * VB_CTRL_N];
+            bool done;
+            if ((rc = all_done(p, st, &done))) return rc;
             if (done) break;
         }
     }
@@ -1323,18 +1480,20 @@ extern "C" int vb_log_prior(const double* prior, int64_t n_row, int n_col, doubl
 }
 
 extern "C" int vb_vireo_fit(const vb_counts* m, const vb_vireo_args* a, void* stream) {
+    if (!m) { vb_set_error("NULL handle"); return VB_E_ARG; }
+    DeviceGuard dg(m->device);
     EmP p;
-    int rc = fill_vireo(m, a, p);
+    int rc = fill_vireo(m, a, p, (cudaStream_t)stream);
     if (rc) return rc;
-    VB_CUDA(cudaSetDevice(m->device));
     return run_loop(m, p, a->poll_every, (cudaStream_t)stream);
 }
 
 extern "C" int vb_vireo_step(const vb_counts* m, const vb_vireo_args* a, int phases, void* stream) {
+    if (!m) { vb_set_error("NULL handle"); return VB_E_ARG; }
+    DeviceGuard dg(m->device);
     EmP p;
-    int rc = fill_vireo(m, a, p);
+    int rc = fill_vireo(m, a, p, (cudaStream_t)stream);
     if (rc) return rc;
-    VB_CUDA(cudaSetDevice(m->device));
     p.ctrl = nullptr;                       // single phases never consult the loop state
     if (p.tiled && (phases & VB_PH_SNP)) {
         rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.RW, p.B, p.RP, (cudaStream_t)stream);
@@ -1345,18 +1504,20 @@ extern "C" int vb_vireo_step(const vb_counts* m, const vb_vireo_args* a, int pha
 }
 
 extern "C" int vb_bmm_fit(const vb_counts* m, const vb_bmm_args* a, void* stream) {
+    if (!m) { vb_set_error("NULL handle"); return VB_E_ARG; }
+    DeviceGuard dg(m->device);
     EmP p;
-    int rc = fill_bmm(m, a, p);
+    int rc = fill_bmm(m, a, p, (cudaStream_t)stream);
     if (rc) return rc;
-    VB_CUDA(cudaSetDevice(m->device));
     return run_loop(m, p, a->poll_every, (cudaStream_t)stream);
 }
 
 extern "C" int vb_bmm_step(const vb_counts* m, const vb_bmm_args* a, int phases, void* stream) {
+    if (!m) { vb_set_error("NULL handle"); return VB_E_ARG; }
+    DeviceGuard dg(m->device);
     EmP p;
-    int rc = fill_bmm(m, a, p);
+    int rc = fill_bmm(m, a, p, (cudaStream_t)stream);
     if (rc) return rc;
-    VB_CUDA(cudaSetDevice(m->device));
     p.ctrl = nullptr;
     if (p.tiled && (phases & VB_PH_SNP)) {
         rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.RW, p.B, p.RP, (cudaStream_t)stream);
@@ -1365,44 +1526,300 @@ extern "C" int vb_bmm_step(const vb_counts* m, const vb_bmm_args* a, int phases,
     return bmm_iteration(m, p, phases, false, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// doublet pass
+// ---------------------------------------------------------------------------------------------
+// column-chunk width of the doublet pass: 0 = row kernels, 16 / 8 = window-segment kernels with the FP64 format
+// that is (or gets) built for this matrix
+static int doublet_chunk(const vb_counts* mc, cudaStream_t st, int* fmt) {
+    vb_counts* m = const_cast<vb_counts*>(mc);
+    *fmt = 0;
+    if (g_path == 1) return 0;
+    if (g_path == 0) {
+        if (m->N < VB_SEG_MIN_NNZ) return 0;
+        for (int f = 0; f <= 2; f += 2) {
+            const int64_t pairs = m->sA[f].n_light + m->sA[f].n_heavy;
+            if (m->sA[f].built && m->sA[f].n_heavy * 4 > pairs) return 0;        // residual-dominated: rows
+        }
+    }
+    if (m->sA[0].built && m->sB[0].built) { *fmt = 0; return 16; }
+    if (m->sA[2].built && m->sB[2].built) { *fmt = 2; return 8; }
+    if (m->seg_failed[0] || vb_seg_build(m, 0, st)) return 0;
+    if (g_path == 0 && m->sA[0].n_heavy * 4 > m->sA[0].n_light + m->sA[0].n_heavy) return 0;
+    *fmt = 0;
+    return 16;
+}
+
+extern "C" int vb_doublet_ws_sizes(const vb_counts* m, int n_donor, int n_gt, int ase_mode, void* stream, vb_doublet_ws* out) {
+    if (!m || !out || n_donor < 1 || n_gt < 1 || n_gt > VB_MAX_GT) { vb_set_error("bad argument"); return VB_E_ARG; }
+    DeviceGuard dg(m->device);
+    const int64_t K2 = n_donor + (int64_t)n_donor * (n_donor - 1) / 2, G2 = n_gt + n_gt * (n_gt - 1) / 2;
+    int fmt;
+    const int cw = doublet_chunk(m, (cudaStream_t)stream, &fmt);
+    const int64_t KP = cw ? (K2 + cw - 1) / cw * cw : K2;
+    out->W = 2 * m->V * KP;
+    out->heavy = cw ? m->C * cw : 0;
+    out->ab2 = (ase_mode ? m->V : 1) * 2 * G2;
+    return VB_OK;
+}
+
 extern "C" int vb_vireo_doublet(const vb_counts* m, int n_donor, int n_gt, int ase_mode,
                                 const double* gt_prob, const double* beta_mu, const double* beta_sum,
                                 const double* log_prior_both, int id_prior_rows,
-                                double* W, double* loglik_out, double* prob_out, double* llr_out,
+                                double* W, double* heavy, double* ab2, const vb_doublet_ws* ws,
+                                double* loglik_out, double* prob_out, double* llr_out,
                                 void* stream) {
-    if (!m || !gt_prob || !beta_mu || !beta_sum || !log_prior_both || !W || !loglik_out || !prob_out || !llr_out) {
+    if (!m || !gt_prob || !beta_mu || !beta_sum || !log_prior_both || !W || !ab2 || !ws || !loglik_out || !prob_out || !llr_out) {
         vb_set_error("NULL argument");
         return VB_E_ARG;
     }
     if (n_gt < 1 || n_gt > VB_MAX_GT || n_donor < 1) { vb_set_error("unsupported n_GT=%d / n_donor=%d", n_gt, n_donor); return VB_E_UNSUPPORTED; }
-    VB_CUDA(cudaSetDevice(m->device));
+    DeviceGuard dg(m->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int K = n_donor, G = n_gt;
     const int K2 = K + K * (K - 1) / 2, G2 = G + G * (G - 1) / 2;
     const int64_t T = ase_mode ? m->V : 1;
-    double* ab2;
-    VB_CUDA(cudaMalloc(&ab2, (size_t)T * 2 * G2 * sizeof(double)));
-    struct Free { void* p; ~Free() { cudaFree(p); } } fr{ab2};
+    int fmt;
+    const int cw = doublet_chunk(m, st, &fmt);
+    const int64_t KP = cw ? (K2 + cw - 1) / cw * cw : K2;
+    if (ws->W < 2 * m->V * KP || ws->ab2 < T * 2 * G2 || (cw && (!heavy || ws->heavy < m->C * cw))) {
+        vb_set_error("doublet workspaces too small for the kernel family in use (see vb_doublet_ws_sizes)");
+        return VB_E_ARG;
+    }
     VB_LAUNCH(7, st, k_doublet_theta<<<(int)((T * G2 + 63) / 64 > 4096 ? 4096 : (T * G2 + 63) / 64), 64, 0, st>>>(beta_mu, beta_sum, T, G, ab2));
     VB_CUDA(cudaGetLastError());
-    VB_LAUNCH(7, st, k_doublet_tables<<<m->grid_elem, VB_THREADS, 0, st>>>(gt_prob, ab2, m->V, K, G, ase_mode, W));
+    VB_LAUNCH(7, st, k_doublet_tables<<<m->grid_elem, VB_THREADS, 0, st>>>(gt_prob, ab2, m->V, K, G, ase_mode, cw, W));
     VB_CUDA(cudaGetLastError());
-    // cell-major pass over column chunks of the K2-wide tables
     EmP p;
     memset(&p, 0, sizeof(p));
-    p.C = m->C; p.V = m->V; p.K = K2; p.B = 1; p.Wt = W; p.ll = loglik_out; p.id_rows = 1;
-    const CountsView v = view_of(m);
-    const int chunk = K2 <= 16 ? (K2 <= 2 ? 2 : K2 <= 4 ? 4 : K2 <= 8 ? 8 : 16) : 128;
-    for (int k0 = 0; k0 < K2; k0 += chunk) {
-        const int width = K2 - k0 < chunk ? K2 - k0 : chunk;
-        int KT, KR;
-        tile_for(width, KT, KR);
-        const dim3 grid(m->grid_cell, 1);
-        VB_LAUNCH(3, st, VB_DISPATCH_TILE(KT, KR, m->wide, k_cell<kt, kr, wd, false><<<grid, VB_THREADS, 0, st>>>(v, p, 1, k0)));
-        VB_CUDA(cudaGetLastError());
+    p.C = m->C; p.V = m->V; p.B = 1; p.ll = loglik_out; p.id_rows = 1;
+    if (cw) {
+        // one pass of the record stream per chunk of cw columns: chunk c's table is W[c] = [2V, cw]
+        p.tiled = 2; p.RW = cw; p.KT = cw; p.K = cw; p.H = heavy;
+        for (int k0 = 0, c = 0; k0 < K2; k0 += cw, ++c) {
+            p.Wt = W + (size_t)c * 2 * m->V * cw;
+            SegPlain pl;
+            pl.out = loglik_out; pl.ld = K2; pl.off = k0; pl.cols = K2 - k0 < cw ? K2 - k0 : cw;
+            const int rc = vb_seg_launch(m, p, 0, GM_PLAIN, 0, &pl, st);
+            if (rc) return rc;
+        }
+    } else {
+        // cell-major pass over column chunks of the K2-wide tables, row kernels
+        p.K = K2; p.Wt = W;
+        const CountsView v = view_of(m);
+        const int chunk = K2 <= 16 ? (K2 <= 2 ? 2 : K2 <= 4 ? 4 : K2 <= 8 ? 8 : 16) : 128;
+        for (int k0 = 0; k0 < K2; k0 += chunk) {
+            const int width = K2 - k0 < chunk ? K2 - k0 : chunk;
+            int KT, KR;
+            tile_for(width, KT, KR);
+            const dim3 grid(m->grid_cell, 1);
+            VB_LAUNCH(3, st, VB_DISPATCH_TILE(KT, KR, m->wide, k_cell<kt, kr, wd, false><<<grid, VB_THREADS, 0, st>>>(v, p, 1, k0)));
+            VB_CUDA(cudaGetLastError());
+        }
     }
     VB_LAUNCH(7, st, k_doublet_softmax<<<m->grid_cell, VB_THREADS, 0, st>>>(loglik_out, log_prior_both, id_prior_rows, m->C, K, K2, prob_out, llr_out));
     VB_CUDA(cudaGetLastError());
-    VB_CUDA(cudaStreamSynchronize(st));
+    return VB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one fit over several GPUs: cells sharded over ranks, NCCL bound at run time
+// ---------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+
+namespace {
+typedef struct ncclComm* nccl_comm_t;
+struct nccl_uid { char internal[VB_COMM_ID_BYTES]; };
+enum { NCCL_DOUBLE = 8, NCCL_SUM = 0 };            // ncclFloat64, ncclSum (nccl.h, stable since 2.0)
+struct NcclApi {
+    void* lib;
+    int (*GetUniqueId)(nccl_uid*);
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid, int);
+    int (*CommDestroy)(nccl_comm_t);
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t);
+    int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t);
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t);
+    const char* (*GetErrorString)(int);
+};
+NcclApi g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+int nccl_load() {
+    if (g_nccl.lib) return VB_OK;
+    // the copy the process already holds (PyTorch loads its bundled libnccl.so.2) is found by its soname
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { vb_set_error("libnccl.so.2 not found: %s", dlerror()); return VB_E_UNSUPPORTED; }
+    NcclApi a;
+    a.lib = h;
+    *(void**)&a.GetUniqueId = dlsym(h, "ncclGetUniqueId");
+    *(void**)&a.CommInitRank = dlsym(h, "ncclCommInitRank");
+    *(void**)&a.CommDestroy = dlsym(h, "ncclCommDestroy");
+    *(void**)&a.AllReduce = dlsym(h, "ncclAllReduce");
+    *(void**)&a.Broadcast = dlsym(h, "ncclBroadcast");
+    *(void**)&a.AllGather = dlsym(h, "ncclAllGather");
+    *(void**)&a.GetErrorString = dlsym(h, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.Broadcast || !a.AllGather || !a.GetErrorString) {
+        vb_set_error("libnccl.so.2 lacks a required symbol");
+        return VB_E_UNSUPPORTED;
+    }
+    g_nccl = a;
+    return VB_OK;
+}
+}  // namespace
+
+struct vb_comm {
+    int device, n_ranks, rank;
+    nccl_comm_t comm;
+};
+
+#define VB_NCCL(call)                                                                              \
+    do {                                                                                           \
+        const int r__ = (call);                                                                    \
+        if (r__ != 0) { vb_set_error("%s failed: %s", #call, g_nccl.GetErrorString(r__)); return VB_E_CUDA; } \
+    } while (0)
+
+extern "C" int vb_comm_unique_id(void* id_out) {
+    if (!id_out) { vb_set_error("NULL argument"); return VB_E_ARG; }
+    const int rc = nccl_load();
+    if (rc) return rc;
+    nccl_uid id;
+    VB_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return VB_OK;
+}
+
+extern "C" int vb_comm_create(int device, int n_ranks, int rank, const void* id, vb_comm** out) {
+    if (!out || n_ranks < 1 || rank < 0 || rank >= n_ranks) { vb_set_error("bad argument"); return VB_E_ARG; }
+    *out = nullptr;
+    vb_comm* c = new vb_comm();
+    c->device = device; c->n_ranks = n_ranks; c->rank = rank; c->comm = nullptr;
+    if (n_ranks > 1) {
+        if (!id) { delete c; vb_set_error("unique id is NULL"); return VB_E_ARG; }
+        int rc = nccl_load();
+        if (rc) { delete c; return rc; }
+        DeviceGuard dg(device);
+        nccl_uid uid;
+        memcpy(&uid, id, sizeof(uid));
+        const int r = g_nccl.CommInitRank(&c->comm, n_ranks, uid, rank);
+        if (r != 0) { vb_set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); delete c; return VB_E_CUDA; }
+    }
+    *out = c;
+    return VB_OK;
+}
+
+extern "C" void vb_comm_destroy(vb_comm* c) {
+    if (!c) return;
+    if (c->comm) { DeviceGuard dg(c->device); g_nccl.CommDestroy(c->comm); }
+    delete c;
+}
+
+extern "C" int vb_comm_allreduce(vb_comm* c, double* buf, int64_t n, void* stream) {
+    if (!c || !buf || n < 0) { vb_set_error("bad argument"); return VB_E_ARG; }
+    if (c->n_ranks == 1 || n == 0) return VB_OK;
+    DeviceGuard dg(c->device);
+    VB_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, NCCL_DOUBLE, NCCL_SUM, c->comm, (cudaStream_t)stream));
+    return VB_OK;
+}
+
+extern "C" int vb_comm_broadcast(vb_comm* c, double* buf, int64_t n, int root, void* stream) {
+    if (!c || !buf || n < 0 || root < 0 || root >= c->n_ranks) { vb_set_error("bad argument"); return VB_E_ARG; }
+    if (c->n_ranks == 1 || n == 0) return VB_OK;
+    DeviceGuard dg(c->device);
+    VB_NCCL(g_nccl.Broadcast(buf, buf, (size_t)n, NCCL_DOUBLE, root, c->comm, (cudaStream_t)stream));
+    return VB_OK;
+}
+
+extern "C" int vb_comm_allgather(vb_comm* c, const double* send, double* recv, int64_t n_per_rank, void* stream) {
+    if (!c || !send || !recv || n_per_rank < 0) { vb_set_error("bad argument"); return VB_E_ARG; }
+    DeviceGuard dg(c->device);
+    if (c->n_ranks == 1) {
+        if (send != recv && n_per_rank) VB_CUDA(cudaMemcpyAsync(recv, send, n_per_rank * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return VB_OK;
+    }
+    if (n_per_rank == 0) return VB_OK;
+    VB_NCCL(g_nccl.AllGather(send, recv, (size_t)n_per_rank, NCCL_DOUBLE, c->comm, (cudaStream_t)stream));
+    return VB_OK;
+}
+
+static int sharded_args(const vb_counts* m, const vb_vireo_args* a, vb_comm* c, double* xbuf, cudaStream_t st, EmP& p) {
+    if (!m || !a || !c || !xbuf) { vb_set_error("NULL argument"); return VB_E_ARG; }
+    if (c->device != m->device) { vb_set_error("communicator and counts live on different devices"); return VB_E_ARG; }
+    if (a->n_batch != 1 || a->ase_mode) { vb_set_error("cell-sharded fit: one restart, no ASE mode (theta per SNP needs no exchange of S)"); return VB_E_UNSUPPORTED; }
+    const int rc = fill_vireo(m, a, p, st, true);
+    if (rc) return rc;
+    p.S1 = xbuf;
+    p.S2 = xbuf + (size_t)p.V * p.K;
+    return VB_OK;
+}
+
+extern "C" int vb_vireo_fit_sharded(const vb_counts* m, const vb_vireo_args* a, vb_comm* c, double* xbuf, void* stream) {
+    if (!m) { vb_set_error("NULL handle"); return VB_E_ARG; }
+    DeviceGuard dg(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    EmP p;
+    int rc = sharded_args(m, a, c, xbuf, st, p);
+    if (rc) return rc;
+    if (p.max_iter < 1) { vb_set_error("max_iter must be >= 1"); return VB_E_ARG; }
+    if (!p.elbo) { vb_set_error("elbo output is NULL"); return VB_E_ARG; }
+    if ((rc = pin_for(VB_CTRL_N))) return rc;
+    const int64_t n_x = 2 * p.V * p.K;
+    double* xs = xbuf + n_x;                                  // {LB_p, KL_ID} of the previous iteration, summed with S
+    VB_CUDA(cudaMemsetAsync(p.ctrl, 0, VB_CTRL_N * sizeof(int32_t), st));
+    VB_CUDA(cudaMemsetAsync(xs, 0, 8 * sizeof(double), st));
+    if (p.tiled) {
+        rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.RW, 1, p.RP, st);
+        if (!rc && p.tiled == 3) rc = vb_seg_quantise_rows(m, p, st);
+        if (rc) return rc;
+    }
+    int poll_every = a->poll_every > 0 ? a->poll_every : 16;
+    const dim3 one(1, 1), elem(m->grid_elem, 1);
+    EmP q = p;
+    q.n_snpblk = m->grid_elem;                                // k_theta sums the block partials of k_theta_sums
+    for (int it = 0; it < p.max_iter; ++it) {
+        if ((rc = launch_snp(m, p, 0, st))) return rc;        // local S1 | S2 (theta sums need the reduced S: not here)
+        if (c->n_ranks > 1) VB_NCCL(g_nccl.AllReduce(xbuf, xbuf, (size_t)(n_x + 2), NCCL_DOUBLE, NCCL_SUM, c->comm, st));
+        if (it > 0) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, 1, xs)); VB_CUDA(cudaGetLastError()); }
+        VB_LAUNCH(0, st, k_theta_sums<<<elem, VB_THREADS, 0, st>>>(p));
+        VB_CUDA(cudaGetLastError());
+        VB_LAUNCH(1, st, k_theta<<<one, 2 * VB_MAX_GT * 32, 0, st>>>(q, 2));
+        VB_CUDA(cudaGetLastError());
+        VB_LAUNCH(2, st, k_gt<<<elem, VB_THREADS, 0, st>>>(p, p.learn_gt));
+        VB_CUDA(cudaGetLastError());
+        if ((rc = launch_cell(m, p, 0, st))) return rc;
+        VB_LAUNCH(7, st, k_xchg_pack<<<1, 64, 0, st>>>(p, xs));
+        VB_CUDA(cudaGetLastError());
+        if ((it + 1) % poll_every == 0 && it + 1 < p.max_iter) {
+            // the flag read here is the verdict on iteration it - 1: identical on every rank (same reduced numbers)
+            bool done;
+            if ((rc = all_done(p, st, &done))) return rc;
+            if (done) break;
+        }
+    }
+    // ELBO and convergence rule of the last executed iteration (a no-op if an earlier one already ended the fit)
+    if (c->n_ranks > 1) VB_NCCL(g_nccl.AllReduce(xs, xs, 2, NCCL_DOUBLE, NCCL_SUM, c->comm, st));
+    VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, 1, xs));
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_vireo_gt_sharded(const vb_counts* m, const vb_vireo_args* a, vb_comm* c, double* xbuf, void* stream) {
+    if (!m) { vb_set_error("NULL handle"); return VB_E_ARG; }
+    DeviceGuard dg(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    EmP p;
+    int rc = sharded_args(m, a, c, xbuf, st, p);
+    if (rc) return rc;
+    p.ctrl = nullptr;
+    if (p.tiled) {
+        rc = vb_pad_rows_launch(m, p.R, p.C, p.K, p.KT, p.RW, 1, p.RP, st);
+        if (!rc && p.tiled == 3) rc = vb_seg_quantise_rows(m, p, st);
+        if (rc) return rc;
+    }
+    if ((rc = launch_snp(m, p, 0, st))) return rc;
+    if (c->n_ranks > 1) VB_NCCL(g_nccl.AllReduce(xbuf, xbuf, (size_t)(2 * p.V * p.K), NCCL_DOUBLE, NCCL_SUM, c->comm, st));
+    VB_LAUNCH(1, st, k_theta<<<dim3(1, 1), 2 * VB_MAX_GT * 32, 0, st>>>(p, 0));
+    VB_CUDA(cudaGetLastError());
+    VB_LAUNCH(2, st, k_gt<<<dim3(m->grid_elem, 1), VB_THREADS, 0, st>>>(p, 1));
+    VB_CUDA(cudaGetLastError());
     return VB_OK;
 }

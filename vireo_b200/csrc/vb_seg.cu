@@ -8,8 +8,8 @@
 //   SNP  pass  S2[i,:] = sum_j (dp-ad)_ij * ID_prob[j,:],  S1[i,:] = sum_j ad_ij * ID_prob[j,:]
 //              (vireo_model.py:168-170,207-209, bmm_model.py:136-138)
 // What bounds such a pass on B200 is the shared-memory crossbar (128 B/clk/SM): every pair needs one
-// table row.  The lane-per-owner kernels of vb_gather.cu spend 1.5 crossbar wavefronts per 128-byte
-// row because a quarter warp is rarely full.  Here
+// table row.  A lane-per-owner layout (the retired gather-stream kernels of round 1) spends 1.5 crossbar
+// wavefronts per 128-byte row because a quarter warp is rarely full.  Here
 //   * 4 lanes share one owner and read its table row with 16-byte loads (two per lane for a 128-byte
 //     FP64 row -- one from each 64-byte half, even lane groups starting in the lower half and odd groups
 //     in the upper half so that the two rows of a wavefront never meet in a bank; one per lane for the
@@ -408,7 +408,7 @@ int vb_seg_build(vb_counts* m, int prec, cudaStream_t st) {
     if (prec < 0 || prec > 2) { vb_set_error("bad table kind"); return VB_E_ARG; }
     if (m->sA[prec].built && m->sB[prec].built) return VB_OK;
     if (m->seg_failed[prec]) return VB_E_UNSUPPORTED;
-    VB_CUDA(cudaSetDevice(m->device));
+    DeviceGuard dg(m->device);
     int rc = seg_build_one<0>(m, m->sA[prec], prec, st);
     if (!rc) rc = seg_build_one<1>(m, m->sB[prec], prec, st);
     if (rc) {
@@ -453,6 +453,30 @@ k_seg_heavy(int64_t n_owner, const int64_t* __restrict__ hptr, const int32_t* __
     }
 }
 
+// replicate [n_row, K] into the rows (RW doubles each) of a gather table: column c holds source column c % KT
+__global__ void __launch_bounds__(VB_THREADS)
+k_pad_rows(const double* __restrict__ src, int64_t n_row, int K, int KT, int RW, double* __restrict__ dst) {
+    const int b = blockIdx.y;
+    const double* __restrict__ S = src + (size_t)b * n_row * K;
+    double* __restrict__ D = dst + (size_t)b * n_row * RW;
+    const int64_t n = n_row * RW;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / RW;
+        const int k = (int)(e % RW) % KT;
+        D[e] = k < K ? S[r * K + k] : 0.0;
+    }
+}
+
+int vb_pad_rows_launch(const vb_counts* m, const double* src, int64_t n_row, int K, int KT, int RW, int B, double* dst,
+                       cudaStream_t st) {
+    int64_t nb = (n_row * RW + VB_THREADS - 1) / VB_THREADS;
+    if (nb > (int64_t)m->sm_count * 8) nb = (int64_t)m->sm_count * 8;
+    if (nb < 1) nb = 1;
+    VB_LAUNCH(7, st, k_pad_rows<<<dim3((unsigned)nb, B), VB_THREADS, 0, st>>>(src, n_row, K, KT, RW, dst));
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
 // ID_prob rows [B*C, 16] -> unsigned 32-bit fixed point, value * (2^32 - 1): a posterior of exactly 1.0 (most
 // cells once the fit has settled) is represented exactly, so the per-SNP sums carry no systematic bias
 __device__ __forceinline__ uint32_t quant_unit(double r) {
@@ -480,6 +504,10 @@ struct SegArgs {
     int wait_hint_ns;    // > 0: suspend-time hint of the window waits
     int64_t table_stride;    // bytes per restart of the gather table
     const unsigned char* table;
+    // GM_PLAIN: the sums of columns [0, plain_cols) go to plain_out[owner * plain_ld + plain_off + column]
+    double* plain_out;
+    int64_t plain_ld;
+    int plain_off, plain_cols;
 };
 
 template <int PREC> struct SegCfg;
@@ -825,6 +853,16 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
                         if (pv > 0.0) r1 += pv * (log(pv) - p.lidp_kl[prow + kk[c]]);
                     }
                 }
+            } else if (sa.mode == GM_PLAIN) {
+                // column chunk of a wider table (doublet pass): plain sums, no softmax
+                if (owner >= 0) {
+                    double* __restrict__ O = sa.plain_out + (size_t)owner * sa.plain_ld + sa.plain_off;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const int col = col0 + (c < 2 ? c : col2 + c - 2);
+                        if (col < sa.plain_cols) O[col] = v[c];
+                    }
+                }
             } else {   // GM_SNP
                 const int64_t i = owner >= 0 ? owner >> 1 : 0;
                 const int al = owner & 1;
@@ -921,7 +959,8 @@ static size_t seg_smem(int prec, int nb, int win_rows) {
 static bool g_seg_attr_set[64] = {false};     // per device: function attributes belong to the context
 
 // ori 0: cell pass (table = p.Wt / p.Wq), ori 1: SNP pass (table = p.RP / p.RPq)
-int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, cudaStream_t st) {
+// mode GM_PLAIN (ori 0, FP64 tables): `plain` says where the sums of this column chunk go
+int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, const SegPlain* plain, cudaStream_t st) {
     const int prec = p.tiled == 3 ? 1 : (p.RW == 8 ? 2 : 0);
     const SegSet& g = ori ? m->sB[prec] : m->sA[prec];
     if (!g.built) { vb_set_error("segment format was not built"); return VB_E_ARG; }
@@ -945,6 +984,10 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
     if (prec != 1) { sa.table = reinterpret_cast<const unsigned char*>(tab64); sa.table_stride = g.n_gather * (prec == 0 ? 128 : 64); }
     else { sa.table = reinterpret_cast<const unsigned char*>(ori ? p.RPq : p.Wq); sa.table_stride = g.n_gather * 64; }
     sa.has_heavy = g.n_heavy > 0;
+    if (mode == GM_PLAIN) {
+        if (!plain || prec == 1 || ori != 0) { vb_set_error("plain segment pass: bad arguments"); return VB_E_ARG; }
+        sa.plain_out = plain->out; sa.plain_ld = plain->ld; sa.plain_off = plain->off; sa.plain_cols = plain->cols;
+    }
     static const int wait_hint = env_int("VIREO_B200_SEG_WAIT_NS", 0);
     sa.wait_hint_ns = wait_hint;
     int grid_x;

@@ -165,10 +165,9 @@ static int to_index(const void* raw, int dtype, int64_t n, TO* out, int sm, cuda
 
 extern "C" void vb_counts_destroy(vb_counts* m) {
     if (!m) return;
-    cudaSetDevice(m->device);
+    DeviceGuard dg(m->device);
     cudaFree(m->cell_ptr); cudaFree(m->cell_idx); cudaFree(m->cell_cnt); cudaFree(m->cell_dp);
     cudaFree(m->snp_ptr); cudaFree(m->snp_idx); cudaFree(m->snp_cnt); cudaFree(m->snp_dp);
-    vb_gather_free(m);
     vb_seg_free(m);
     delete m;
 }
@@ -185,14 +184,7 @@ extern "C" int64_t vb_counts_info(const vb_counts* m, int what) {
         case 6: return m->grid_cell;
         case 7: return m->grid_snp;
         case 8: return m->grid_elem;
-        case 9: return m->gA.built && m->gB.built;
-        case 10: return m->gA.n_rec;
-        case 11: return m->gB.n_rec;
-        case 12: return m->gA.n_heavy;
-        case 13: return m->gA.bytes + m->gB.bytes;
-        case 14: { int g = 0, w = 0; if (m->gA.built) vb_gather_geometry(m, m->gA, &g, &w); return g; }
-        case 15: { int g = 0, w = 0; if (m->gB.built) vb_gather_geometry(m, m->gB, &g, &w); return g; }
-        case 16: return m->gA.n_light;
+        case 60: return m->auto_fallback;
         // window-segment formats: 20 + 10 * precision + {0 built, 1 / 2 super-steps of the cell / SNP pass,
         // 3 / 4 largest reads of one owner's stream (cell / SNP pass), 5 / 6 grid.x, 7 bytes, 8 residual pairs, 9 stream pairs}
         default: break;
@@ -215,6 +207,97 @@ extern "C" int64_t vb_counts_info(const vb_counts* m, int what) {
     return -1;
 }
 
+extern "C" const char* vb_counts_note(const vb_counts* m) { return m ? m->seg_error : ""; }
+
+// SNP-major orientation from the finished cell-major arrays (stable radix sort of the nnz positions by SNP id) and the
+// launch geometry of the row kernels
+static int finish_counts(vb_counts* m, cudaStream_t st) {
+    const int sm = m->sm_count;
+    const int64_t C = m->C, V = m->V, N = m->N;
+    const int64_t Nz = N ? N : 1;
+    Scratch tmp;
+    VB_CUDA(cudaMalloc(&m->snp_ptr, (V + 1) * sizeof(int64_t)));
+    VB_CUDA(cudaMalloc(&m->snp_idx, Nz * sizeof(int32_t)));
+    VB_CUDA(cudaMalloc(&m->snp_cnt, Nz * sizeof(uint32_t)));
+    if (m->wide) VB_CUDA(cudaMalloc(&m->snp_dp, Nz * sizeof(uint32_t)));
+    if (N) {
+        uint32_t *keys_out, *vals_in, *vals_out;
+        VB_CUDA(cudaMalloc(&keys_out, N * sizeof(uint32_t))); tmp.keep(keys_out);
+        VB_CUDA(cudaMalloc(&vals_in, N * sizeof(uint32_t))); tmp.keep(vals_in);
+        VB_CUDA(cudaMalloc(&vals_out, N * sizeof(uint32_t))); tmp.keep(vals_out);
+        k_iota<<<grid_for(N, sm), 256, 0, st>>>(vals_in, N);
+        VB_CUDA(cudaGetLastError());
+        int bits = 1;
+        while ((1ll << bits) < V) ++bits;
+        size_t tb = 0;
+        const uint32_t* keys_in = (const uint32_t*)m->cell_idx;
+        VB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in, keys_out, vals_in, vals_out, (int64_t)N, 0, bits, st));
+        void* cub_tmp;
+        VB_CUDA(cudaMalloc(&cub_tmp, tb ? tb : 8)); tmp.keep(cub_tmp);
+        VB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, tb, keys_in, keys_out, vals_in, vals_out, (int64_t)N, 0, bits, st));
+        k_gather_snp_major<<<grid_for(N, sm), 256, 0, st>>>(vals_out, N, m->cell_ptr, C, m->cell_cnt, m->cell_dp,
+                                                          m->snp_idx, m->snp_cnt, m->snp_dp);
+        VB_CUDA(cudaGetLastError());
+        k_row_starts<<<grid_for(V + 1, sm), 256, 0, st>>>(keys_out, N, V, m->snp_ptr);
+        VB_CUDA(cudaGetLastError());
+    } else {
+        VB_CUDA(cudaMemsetAsync(m->snp_ptr, 0, (V + 1) * sizeof(int64_t), st));
+    }
+    VB_CUDA(cudaStreamSynchronize(st));
+
+    // launch geometry: one warp per row, persistent grid capped at 8 CTAs per SM
+    auto rows_grid = [&](int64_t rows) {
+        int64_t b = (rows + VB_WARPS - 1) / VB_WARPS;
+        if (b < 1) b = 1;
+        const int64_t cap = (int64_t)sm * 8;
+        return (int)(b > cap ? cap : b);
+    };
+    m->grid_cell = rows_grid(C);
+    m->grid_snp = rows_grid(V);
+    m->grid_elem = sm * 8;
+    m->bytes = (C + 1 + V + 1) * 8 + N * (m->wide ? 24 : 16);
+    return VB_OK;
+}
+
+__global__ void k_rebase_ptr(const int64_t* __restrict__ in, int64_t n, int64_t base, int64_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = in[i] - base;
+}
+
+extern "C" int vb_counts_slice(const vb_counts* src, int64_t c0, int64_t c1, void* stream, vb_counts** out) {
+    if (!out) { vb_set_error("out is NULL"); return VB_E_ARG; }
+    *out = nullptr;
+    if (!src || c0 < 0 || c1 < c0 || c1 > src->C) { vb_set_error("bad cell range [%lld, %lld)", (long long)c0, (long long)c1); return VB_E_ARG; }
+    DeviceGuard dg(src->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t ends[2] = {0, 0};
+    VB_CUDA(cudaMemcpyAsync(&ends[0], src->cell_ptr + c0, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VB_CUDA(cudaMemcpyAsync(&ends[1], src->cell_ptr + c1, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VB_CUDA(cudaStreamSynchronize(st));
+    vb_counts* m = new vb_counts();
+    memset(m, 0, sizeof(*m));
+    m->device = src->device; m->sm_count = src->sm_count; m->C = c1 - c0; m->V = src->V; m->N = ends[1] - ends[0];
+    m->wide = src->wide;       // keep the record layout of the parent (a shard without wide counts still reads them correctly)
+    struct Guard { vb_counts* m; ~Guard() { if (m) vb_counts_destroy(m); } } guard{m};
+    const int64_t Nz = m->N ? m->N : 1;
+    VB_CUDA(cudaMalloc(&m->cell_ptr, (m->C + 1) * sizeof(int64_t)));
+    VB_CUDA(cudaMalloc(&m->cell_idx, Nz * sizeof(int32_t)));
+    VB_CUDA(cudaMalloc(&m->cell_cnt, Nz * sizeof(uint32_t)));
+    if (m->wide) VB_CUDA(cudaMalloc(&m->cell_dp, Nz * sizeof(uint32_t)));
+    k_rebase_ptr<<<grid_for(m->C + 1, m->sm_count), 256, 0, st>>>(src->cell_ptr + c0, m->C + 1, ends[0], m->cell_ptr);
+    VB_CUDA(cudaGetLastError());
+    if (m->N) {
+        VB_CUDA(cudaMemcpyAsync(m->cell_idx, src->cell_idx + ends[0], m->N * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        VB_CUDA(cudaMemcpyAsync(m->cell_cnt, src->cell_cnt + ends[0], m->N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        if (m->wide) VB_CUDA(cudaMemcpyAsync(m->cell_dp, src->cell_dp + ends[0], m->N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    const int rc = finish_counts(m, st);
+    if (rc) return rc;
+    guard.m = nullptr;
+    *out = m;
+    return VB_OK;
+}
+
 extern "C" int vb_counts_create(int device, int64_t n_cell, int64_t n_var,
                                 const void* dp_indptr, int indptr_dtype,
                                 const void* dp_indices, int indices_dtype,
@@ -233,7 +316,7 @@ extern "C" int vb_counts_create(int device, int64_t n_cell, int64_t n_var,
         vb_set_error("NULL input array");
         return VB_E_ARG;
     }
-    VB_CUDA(cudaSetDevice(device));
+    DeviceGuard dg(device);
     cudaStream_t st = (cudaStream_t)stream;
     cudaDeviceProp prop;
     VB_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -301,47 +384,7 @@ extern "C" int vb_counts_create(int device, int64_t n_cell, int64_t n_var,
         if (N) { k_pack<<<grid_for(N, sm), 256, 0, st>>>(ad_at_dp, dp_val, m->cell_cnt, N); VB_CUDA(cudaGetLastError()); }
     }
 
-    // ---- SNP-major orientation: stable radix sort of nnz positions by SNP id
-    VB_CUDA(cudaMalloc(&m->snp_ptr, (V + 1) * sizeof(int64_t)));
-    VB_CUDA(cudaMalloc(&m->snp_idx, Nz * sizeof(int32_t)));
-    VB_CUDA(cudaMalloc(&m->snp_cnt, Nz * sizeof(uint32_t)));
-    if (m->wide) VB_CUDA(cudaMalloc(&m->snp_dp, Nz * sizeof(uint32_t)));
-    if (N) {
-        uint32_t *keys_out, *vals_in, *vals_out;
-        VB_CUDA(cudaMalloc(&keys_out, N * sizeof(uint32_t))); tmp.keep(keys_out);
-        VB_CUDA(cudaMalloc(&vals_in, N * sizeof(uint32_t))); tmp.keep(vals_in);
-        VB_CUDA(cudaMalloc(&vals_out, N * sizeof(uint32_t))); tmp.keep(vals_out);
-        k_iota<<<grid_for(N, sm), 256, 0, st>>>(vals_in, N);
-        VB_CUDA(cudaGetLastError());
-        int bits = 1;
-        while ((1ll << bits) < V) ++bits;
-        size_t tb = 0;
-        const uint32_t* keys_in = (const uint32_t*)m->cell_idx;
-        VB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in, keys_out, vals_in, vals_out, (int64_t)N, 0, bits, st));
-        void* cub_tmp;
-        VB_CUDA(cudaMalloc(&cub_tmp, tb ? tb : 8)); tmp.keep(cub_tmp);
-        VB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, tb, keys_in, keys_out, vals_in, vals_out, (int64_t)N, 0, bits, st));
-        k_gather_snp_major<<<grid_for(N, sm), 256, 0, st>>>(vals_out, N, m->cell_ptr, C, m->cell_cnt, m->cell_dp,
-                                                          m->snp_idx, m->snp_cnt, m->snp_dp);
-        VB_CUDA(cudaGetLastError());
-        k_row_starts<<<grid_for(V + 1, sm), 256, 0, st>>>(keys_out, N, V, m->snp_ptr);
-        VB_CUDA(cudaGetLastError());
-    } else {
-        VB_CUDA(cudaMemsetAsync(m->snp_ptr, 0, (V + 1) * sizeof(int64_t), st));
-    }
-    VB_CUDA(cudaStreamSynchronize(st));
-
-    // ---- launch geometry: one warp per row, persistent grid capped at 8 CTAs per SM
-    auto rows_grid = [&](int64_t rows) {
-        int64_t b = (rows + VB_WARPS - 1) / VB_WARPS;
-        if (b < 1) b = 1;
-        const int64_t cap = (int64_t)sm * 8;
-        return (int)(b > cap ? cap : b);
-    };
-    m->grid_cell = rows_grid(C);
-    m->grid_snp = rows_grid(V);
-    m->grid_elem = sm * 8;
-    m->bytes = (C + 1 + V + 1) * 8 + N * (m->wide ? 24 : 16);
+    if ((rc = finish_counts(m, st))) return rc;
     guard.m = nullptr;
     *out = m;
     return VB_OK;
@@ -375,7 +418,7 @@ __global__ void k_sum_partials(const double* __restrict__ part, int n, double* _
 
 extern "C" int vb_binom_const(const vb_counts* m, double* scratch, double* out_host, void* stream) {
     if (!m || !scratch || !out_host) { vb_set_error("NULL argument"); return VB_E_ARG; }
-    VB_CUDA(cudaSetDevice(m->device));
+    DeviceGuard dg(m->device);
     cudaStream_t st = (cudaStream_t)stream;
     int g = grid_for(m->N, m->sm_count);
     if (g > 1023) g = 1023;

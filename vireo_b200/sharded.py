@@ -1,26 +1,29 @@
 """Cell-sharded single fit: ONE ``Vireo`` fit data-parallel over cells, for the fits that restart
 sharding cannot spread -- the final fit of ``vireo_wrap`` (reference vireoSNP/utils/vireo_wrap.py:94) and the
-GT-given mode, which has a single restart (vireo_wrap.py:48-50).
+GT-given mode, which has a single restart (vireo_wrap.py:48-50) -- plus the doublet pass that follows
+(vireo_doublet.py:39-75), whose likelihood block is independent per cell.
 
-Every rank stages the count columns of its own cells and keeps ``ID_prob`` for them; ``GT_prob`` and theta are
-replicated.  One EM iteration (reference vireo_model.py:257-264):
+Every rank holds the staged count columns of its own cells (cut on the device from the full staged matrices,
+``vb_counts_slice``) and keeps ``ID_prob`` for them; ``GT_prob`` and theta are replicated.  The whole loop runs inside
+the library (``vb_vireo_fit_sharded``): per EM iteration (reference vireo_model.py:257-264)
 
     SNP pass on the local cells      S1_r = AD_r @ ID_prob_r,  S2_r = (DP_r - AD_r) @ ID_prob_r
-    ONE all-reduce (NCCL, sum)       S1 | S2, 2 * n_var * n_donor doubles   <- the path's real exchange step
+    ONE all-reduce (NCCL, sum)       S1 | S2 | {LB_p, KL_ID} of the previous iteration   <- the path's exchange step
+    ELBO + convergence rule of the previous iteration, on the device, identical on every rank
     theta, GT update                 identical on every rank (same inputs, same kernels)
-    cell pass on the local cells     ID_prob_r, and the local parts of LB_p and KL_ID
-    all-reduce of those 2 scalars    ELBO = sum_r (LB_p - KL_ID)_r - KL_GT - KL_theta, convergence on the host
+    cell pass on the local cells     ID_prob_r and the local parts of LB_p and KL_ID
 
 The convergence rule, the ``ELBO[:it]`` quirk and the binomial constant follow the reference exactly
-(vireo_model.py:266-276,313).  Without an initialised process group the same code runs over ``n_local`` shards
-inside one process (the reduction is then a plain sum), which is how the single-GPU test exercises it.
+(vireo_model.py:266-276,313); the constant is the single float32 sum over the FULL matrices (every rank has them
+staged), as in the reference.  On a single rank the same library loop runs without the exchange.
 """
 import copy
+import ctypes as C
 
 import numpy as np
 
 from . import _engine, _lib
-from .dist import _dist, world
+from .dist import comm, world
 
 
 def cell_shards(indptr, n_shard):
@@ -34,42 +37,18 @@ def cell_shards(indptr, n_shard):
     return np.maximum.accumulate(bounds)
 
 
-def converged(elbo, it, min_iter, max_iter, eps, verbose):
-    """The reference's per-iteration rule (vireo_model.py:266-274); True = break after this iteration."""
-    if it > min_iter:
-        if elbo[it] < elbo[it - 1] - 1e-6:
-            if verbose:
-                print("Warning: Lower bound decreases!\n")
-        elif it == max_iter - 1:
-            if verbose:
-                print("Warning: VB did not converge!\n")
-        elif elbo[it] - elbo[it - 1] < eps:
-            return True
-    return False
-
-
-_SHARDS = {}
-
-
-def _shard_counts(AD, DP, c0, c1):
-    """Staged counts of the cell range [c0, c1), cached like ``_engine.stage`` (by the identity and a fingerprint of
-    the full matrices), so that repeated sharded fits slice and upload nothing."""
-    import weakref
-    dev = _engine.default_device()
-    key = (id(AD), id(DP), int(c0), int(c1), dev)
-    fp = (_engine._fingerprint(AD), _engine._fingerprint(DP))
-    hit = _SHARDS.get(key)
-    if hit is not None and hit[0] == fp and hit[1]._h is not None:
-        return hit[1]
-    counts = _engine.StagedCounts(AD[:, c0:c1], DP[:, c0:c1], dev)
-    if len(_SHARDS) >= 16:
-        _SHARDS.pop(next(iter(_SHARDS)))[1].close()
-    _SHARDS[key] = (fp, counts)
-    try:
-        weakref.finalize(DP, _SHARDS.pop, key, None)
-    except TypeError:
-        pass
-    return counts
+def shard_of(counts):
+    """(StagedCounts of this rank's cells, c0, c1, bounds of all ranks) -- cut once per staged matrix and world."""
+    rank, ws = world()
+    key = (ws, rank)
+    hit = counts._shards.get(key)
+    if hit is not None and hit[0]._h is not None:
+        return hit
+    bounds = cell_shards(counts.indptr, ws)
+    c0, c1 = int(bounds[rank]), int(bounds[rank + 1])
+    local = counts if ws == 1 else counts.slice_cells(c0, c1)
+    counts._shards[key] = (local, c0, c1, bounds)
+    return counts._shards[key]
 
 
 def _local_model(model, c0, c1):
@@ -81,120 +60,94 @@ def _local_model(model, c0, c1):
     return loc
 
 
-def fit_cell_sharded(model, AD, DP, max_iter=200, min_iter=5, epsilon_conv=1e-2, delay_fit_theta=0, verbose=True,
-                     n_local=1):
-    """``model.fit(AD, DP, ...)`` with the cells sharded over the ranks of the initialised process group (times
-    ``n_local`` shards per process).  Every rank passes the same model state and the full matrices; on return every
-    rank holds the complete fitted state and the same ``ELBO_``."""
+def _gather_rows(cm, local, n_cols, bounds, dev):
+    """All-gather of per-rank row blocks [c1 - c0, n_cols] (device tensor `local`) -> host array [n_cell, n_cols]."""
     t = _engine.torch()
-    from scipy.sparse import csc_matrix, isspmatrix_csc
+    ws = cm.world
+    per = int(np.max(np.diff(bounds))) * n_cols
+    send = t.zeros(max(per, 1), dtype=t.float64, device="cuda:%d" % dev)
+    send[:local.numel()].copy_(local.reshape(-1))
+    recv = t.empty(max(per, 1) * ws, dtype=t.float64, device="cuda:%d" % dev)
+    _lib.check(_lib.load().vb_comm_allgather(cm.handle, _engine._ptr(send), _engine._ptr(recv), max(per, 1),
+                                             _engine._stream(dev)))
+    host = _engine._to_host(recv)
+    if ws == 1:
+        return host[:local.numel()].reshape(-1, n_cols)
+    out = np.empty((int(bounds[-1]), n_cols))
+    for r in range(ws):
+        c0, c1 = int(bounds[r]), int(bounds[r + 1])
+        out[c0:c1] = host[r * per:r * per + (c1 - c0) * n_cols].reshape(c1 - c0, n_cols)
+    return out
+
+
+def fit_cell_sharded(model, AD, DP=None, max_iter=200, min_iter=5, epsilon_conv=1e-2, delay_fit_theta=0, verbose=True,
+                     poll_every=0):
+    """``model.fit(AD, DP, ...)`` with the cells sharded over the ranks enabled by ``vireo_b200.dist.enable()``.
+    Every rank passes the same model state and the same matrices (or their ``StagedCounts``); on return every rank
+    holds the complete fitted state and the same ``ELBO_``."""
+    t = _engine.torch()
     if getattr(model, "ASE_mode", False):
         raise NotImplementedError("cell-sharded fit: ASE mode keeps theta per SNP; use model.fit")
-    if not isspmatrix_csc(AD):
-        AD = csc_matrix(AD)
-    if not isspmatrix_csc(DP):
-        DP = csc_matrix(DP)
-    rank, ws = world()
-    d = _dist()
-    n_shard = ws * n_local
-    bounds = cell_shards(DP.indptr, n_shard)
-    mine = [rank * n_local + i for i in range(n_local)]
-    K, G, V = int(model.n_donor), int(model.n_GT), int(model.n_var)
-
-    batches, consts = [], 0.0
-    for sidx in mine:
-        c0, c1 = int(bounds[sidx]), int(bounds[sidx + 1])
-        counts = _shard_counts(AD, DP, c0, c1)
-        consts += float(counts.binom_const())
-        batches.append((c0, c1, _engine.VireoBatch(counts, [_local_model(model, c0, c1)])))
-    dev = batches[0][2].dev
-    nccl = d is not None and d.get_backend() == "nccl"
-
-    def reduce_(tensors):
-        """sum over the local shards, then over the ranks; every shard's tensor ends up holding the total"""
-        tot = tensors[0]
-        for x in tensors[1:]:
-            tot.add_(x)
-        if d is not None:
-            if nccl:
-                d.all_reduce(tot)
-            else:                                  # gloo: through the host
-                h = tot.cpu()
-                d.all_reduce(h)
-                tot.copy_(h)
-        for x in tensors[1:]:
-            x.copy_(tot)
-
-    PH = _lib
-    # ELBO terms of every iteration stay on the device ({LB_p, KL_ID} summed over shards and ranks, KL_GT, KL_theta);
-    # the host reads them back only when the reference's rule could stop the loop (it > min_iter), so the first
-    # min_iter + 1 iterations -- all of them in a fixed-length fit -- are enqueued without a single synchronisation
-    terms = t.zeros((max_iter, 4), dtype=t.float64, device="cuda:%d" % dev)
-    elbo = np.zeros(max_iter)
-    known = 0                      # iterations whose ELBO is on the host already
-
-    def fetch(upto):
-        nonlocal known
-        if upto > known:
-            h = terms[known:upto].cpu().numpy()
-            elbo[known:upto] = h[:, 0] - h[:, 1] - h[:, 2] - h[:, 3]
-            known = upto
-
-    it = 0
-    for it in range(max_iter):
-        for _, _, b in batches:
-            b.run_step(PH.PH_SNP)
-        reduce_([b.S12 for _, _, b in batches])
-        phases = PH.PH_THETA_SUMS | PH.PH_ID | PH.PH_ELBO
-        if model.learn_theta and it >= delay_fit_theta:
-            phases |= PH.PH_THETA
-        if model.learn_GT:
-            phases |= PH.PH_GT
-        for _, _, b in batches:
-            b.run_step(phases)
-        # scal = {ELBO, LB_p, KL_ID, KL_GT, KL_theta}: LB_p and KL_ID are sums over cells
-        parts = [b.scal[1:3].clone() for _, _, b in batches]
-        reduce_(parts)
-        terms[it, 0:2].copy_(parts[0])
-        terms[it, 2:4].copy_(batches[0][2].scal[3:5])
-        if it > min_iter:
-            fetch(it + 1)
-            if converged(elbo, it, min_iter, max_iter, epsilon_conv, verbose):
-                break
-    fetch(it + 1)
+    counts = _engine.stage(AD, DP)
+    local, c0, c1, bounds = shard_of(counts)
+    dev = counts.device
+    cm = comm(dev)
+    K, V = int(model.n_donor), int(model.n_var)
+    batch = _engine.VireoBatch(local, [_local_model(model, c0, c1)])
+    xbuf = t.zeros(2 * V * K + 8, dtype=t.float64, device="cuda:%d" % dev)
+    a = batch.args(max_iter, min_iter, epsilon_conv, delay_fit_theta, poll_every)
+    _lib.check(_lib.load().vb_vireo_fit_sharded(local.handle, C.byref(a), cm.handle, _engine._ptr(xbuf),
+                                                _engine._stream(dev)))
+    batch.max_iter = max_iter
+    elbo, last = batch.traces()[0]
+    _engine.replay_convergence(elbo, last, max_iter, min_iter, epsilon_conv, False, verbose)
 
     # results: GT_prob and theta are replicated, ID_prob is gathered
-    b0 = batches[0][2]
-    b0.download(("GT_prob", "theta"))
-    model.GT_prob = b0.models[0].GT_prob
-    model.beta_mu, model.beta_sum = b0.models[0].beta_mu, b0.models[0].beta_sum
-    ID = np.empty((int(model.n_cell), K))
-    per = int(np.max(np.diff(bounds))) * K
-    send = t.zeros(max(per, 1) * n_local, dtype=t.float64, device="cuda:%d" % dev)
-    for i, (c0, c1, b) in enumerate(batches):
-        send[i * per:i * per + (c1 - c0) * K].copy_(b.id_prob[:(c1 - c0) * K])
-    if d is not None:
-        recv = [t.empty_like(send) for _ in range(ws)]
-        if nccl:
-            d.all_gather(recv, send)
-            recv = [r.cpu().numpy() for r in recv]
-        else:
-            hs = send.cpu()
-            hr = [t.empty_like(hs) for _ in range(ws)]
-            d.all_gather(hr, hs)
-            recv = [r.numpy() for r in hr]
-    else:
-        recv = [send.cpu().numpy()]
-    for r in range(ws):
-        for i in range(n_local):
-            c0, c1 = int(bounds[r * n_local + i]), int(bounds[r * n_local + i + 1])
-            ID[c0:c1] = recv[r][i * per:i * per + (c1 - c0) * K].reshape(c1 - c0, K)
-    model.ID_prob = ID
-    const = consts
-    if d is not None:
-        ct = t.tensor([consts], dtype=t.float64, device="cuda:%d" % dev if nccl else "cpu")
-        d.all_reduce(ct)
-        const = float(ct.item())
-    trace = elbo[:it].copy() + const            # the reference returns ELBO[:it] (vireo_model.py:276) + constant (:313)
+    model.ID_prob = _gather_rows(cm, batch.id_prob, K, bounds, dev)
+    if model.learn_GT:
+        model.GT_prob = _engine._to_host(batch.gt_prob).reshape(V, K, int(model.n_GT))
+    th = _engine._to_host(batch.state[batch.id_prob.numel() + batch.gt_prob.numel():])
+    n_th = batch.beta_mu.numel()
+    model.beta_mu, model.beta_sum = th[:n_th].reshape(1, -1).copy(), th[n_th:].reshape(1, -1).copy()
+    batch.close()
+    trace = elbo[:last].copy() + counts.binom_const()      # ELBO[:it] (vireo_model.py:276) + the constant (:313)
     model.ELBO_ = np.append(model.ELBO_, trace)
     return trace
+
+
+def predict_doublet_sharded(vobj, AD, DP=None, update_GT=True, update_ID=True, doublet_rate_prior=None):
+    """``predict_doublet`` (reference vireoSNP/utils/vireo_doublet.py:11-82) with the cells sharded over the enabled
+    ranks: every rank runs the doublet likelihood block and softmax on its own cells, ONE all-gather brings the
+    posteriors and LLRs together, and the closing ``update_GT_prob`` (:75) is a local SNP pass + one all-reduce of
+    S1 | S2.  Returns what ``predict_doublet`` returns, identical on every rank."""
+    from .vireo_doublet import doublet_log_prior
+    t = _engine.torch()
+    counts = _engine.stage(AD, DP)
+    local, c0, c1, bounds = shard_of(counts)
+    dev = counts.device
+    cm = comm(dev)
+    K, V, G = int(vobj.n_donor), int(vobj.n_var), int(vobj.n_GT)
+    K2 = K + K * (K - 1) // 2
+    log_prior_both = doublet_log_prior(vobj, counts.n_cell, doublet_rate_prior)
+    if log_prior_both.shape[0] > 1:
+        log_prior_both = log_prior_both[c0:c1]
+    pr, llr = _engine.doublet_pass(local, np.asarray(vobj.GT_prob, dtype=np.float64), vobj.beta_mu, vobj.beta_sum,
+                                   log_prior_both, vobj.ASE_mode, keep_device=True)
+    both = t.cat([pr.view(local.n_cell, K2), llr.view(local.n_cell, 1)], dim=1).contiguous()
+    full = _gather_rows(cm, both, K2 + 1, bounds, dev)
+    prob_both, llr_all = np.ascontiguousarray(full[:, :K2]), np.ascontiguousarray(full[:, K2])
+    if update_ID:
+        vobj.ID_prob = prob_both[:, :K].copy()
+    if update_GT:
+        if update_ID:
+            loc = _local_model(vobj, c0, c1)
+            batch = _engine.VireoBatch(local, [loc])
+            xbuf = t.zeros(2 * V * K + 8, dtype=t.float64, device="cuda:%d" % dev)
+            a = batch.args()
+            _lib.check(_lib.load().vb_vireo_gt_sharded(local.handle, C.byref(a), cm.handle, _engine._ptr(xbuf),
+                                                       _engine._stream(dev)))
+            vobj.GT_prob = _engine._to_host(batch.gt_prob).reshape(V, K, G)
+            batch.close()
+        else:
+            print("For update_GT, please turn on update_ID.")
+    return prob_both[:, K:], prob_both[:, :K], llr_all

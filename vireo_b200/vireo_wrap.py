@@ -4,9 +4,10 @@ and doublet prediction.  ``vireo_flock`` is the pre-0.3 name of the same functio
 (reference doc/release.rst:138-140).
 
 What changes underneath: the ``n_init`` warm-up fits run as device batches on the staged count
-matrices (and are sharded over ranks when ``torch.distributed`` is initialised, see ``dist.py``)
-instead of a ``multiprocessing.Pool`` of pickled models (vireo_wrap.py:74-83).  ``nproc`` is accepted
-and ignored.
+matrices instead of a ``multiprocessing.Pool`` of pickled models (vireo_wrap.py:74-83); ``nproc`` is
+accepted and ignored.  After ``vireo_b200.dist.enable()`` (one process per GPU, see ``dist.py``) the
+warm-ups are sharded over the ranks by restart, and the fits that follow model selection -- which restart
+sharding cannot spread -- and the doublet pass are sharded by cell (``sharded.py``).
 """
 import sys
 
@@ -15,10 +16,23 @@ import os
 import numpy as np
 
 from . import _engine
-from .dist import gather_restarts, shard_restarts, world
+from .dist import check_same_problem, gather_restarts, shard_restarts, world
 from .vireo_base import donor_select, optimal_match
 from .vireo_doublet import predict_doublet
 from .vireo_model import Vireo
+
+
+# phase timing for bench.py (`wrap` key): off unless PHASES["on"]; every mark synchronises the device
+PHASES = {"on": False, "last": 0.0, "t": {}}
+
+
+def _mark(name, device):
+    if PHASES["on"]:
+        import time
+        _engine.torch().cuda.synchronize(device)
+        now = time.perf_counter()
+        PHASES["t"][name] = PHASES["t"].get(name, 0.0) + now - PHASES["last"]
+        PHASES["last"] = now
 
 
 def _fit_batched(counts, models, max_iter, min_iter, delay_fit_theta):
@@ -63,9 +77,26 @@ def vireo_wrap(AD, DP, GT_prior=None, n_donor=None, learn_GT=True, n_init=20,
         raise NotImplementedError("check_ambient (\"under development\" in the reference, vireo.py:79-81) "
                                   "is outside the accelerated path")
 
+    if PHASES["on"]:
+        import time
+        PHASES["t"], PHASES["last"] = {}, time.perf_counter()
     counts = _engine.stage(AD, DP)
     n_var, n_cell = counts.shape
+    rank, ws = world()
+    check_same_problem(n_cell, n_var, counts.nnz, n_donor, n_init, random_seed, n_extra_donor,
+                       float(counts.binom_const()), device=counts.device)
+    # fits of ONE model are sharded by cell over the ranks (ASE mode keeps theta per SNP and stays on one GPU;
+    # VIREO_B200_SHARD_CELLS=0 keeps every rank fitting the full matrices redundantly)
+    shard_cells = ws > 1 and not kwargs.get("ASE_mode", False) and os.environ.get("VIREO_B200_SHARD_CELLS", "1") != "0"
 
+    def fit_one(model, **kw):
+        if shard_cells:
+            from .sharded import fit_cell_sharded
+            fit_cell_sharded(model, counts, None, verbose=False, **kw)
+        else:
+            model.fit(counts, None, verbose=False, **kw)
+
+    _mark("stage_and_check", counts.device)
     if random_seed is not None:
         np.random.seed(random_seed)
 
@@ -83,11 +114,12 @@ def vireo_wrap(AD, DP, GT_prior=None, n_donor=None, learn_GT=True, n_init=20,
         m.set_prior(GT_prior=GT_prior_use)
         models.append(m)
 
+    _mark("draw_inits", counts.device)
     mine = shard_restarts(n_init)
     _fit_batched(counts, [models[i] for i in mine], max_iter_init, 5, delay_fit_theta)
+    _mark("warmups", counts.device)
 
     # model selection: one all-gather of the final ELBOs, winner's state broadcast by its owner
-    rank, ws = world()
     final = np.array([models[i].ELBO_[-1] if i in mine else -np.inf for i in range(n_init)])
     results = {i: dict(ID_prob=models[i].ID_prob, GT_prob=models[i].GT_prob, beta_mu=models[i].beta_mu,
                        beta_sum=models[i].beta_sum, ELBO_=models[i].ELBO_) for i in mine}
@@ -98,23 +130,19 @@ def vireo_wrap(AD, DP, GT_prior=None, n_donor=None, learn_GT=True, n_init=20,
         modelCA.ID_prob, modelCA.GT_prob = state["ID_prob"], state["GT_prob"]
         modelCA.beta_mu, modelCA.beta_sum = state["beta_mu"], state["beta_sum"]
         modelCA.ELBO_ = np.atleast_1d(state["ELBO_"])
+    _mark("select", counts.device)
 
     if n_extra_donor == 0:
-        if ws > 1 and os.environ.get("VIREO_B200_SHARD_CELLS", "0") == "1" and not modelCA.ASE_mode \
-                and not isinstance(AD, _engine.StagedCounts):
-            # the one fit restart sharding cannot spread: data-parallel over cells, one all-reduce per iteration
-            from .sharded import fit_cell_sharded
-            fit_cell_sharded(modelCA, AD, DP, min_iter=5, verbose=False)
-        else:
-            modelCA.fit(counts, None, min_iter=5, verbose=False)
+        fit_one(modelCA, min_iter=5)          # <= 200 iterations: the fit that dominates the call (vireo_wrap.py:93-94)
     else:
         _ID_prob = donor_select(modelCA.GT_prob, modelCA.ID_prob, n_donor, mode=extra_donor_mode)
         modelCA = Vireo(n_var=n_var, n_cell=n_cell, n_donor=n_donor, learn_GT=learn_GT,
                         GT_prob_init=GT_prior_use, ID_prob_init=_ID_prob,
                         beta_mu_init=modelCA.beta_mu, beta_sum_init=modelCA.beta_sum, **kwargs)
         modelCA.set_prior(GT_prior=GT_prior_use)
-        modelCA.fit(counts, None, min_iter=5, delay_fit_theta=delay_fit_theta, verbose=False)
+        fit_one(modelCA, min_iter=5, delay_fit_theta=delay_fit_theta)
 
+    _mark("final_fit", counts.device)
     print("[vireo] lower bound ranges [%.1f, %.1f, %.1f]"
           % (np.min(elbo_all), np.median(elbo_all), np.max(elbo_all)))
 
@@ -124,7 +152,7 @@ def vireo_wrap(AD, DP, GT_prior=None, n_donor=None, learn_GT=True, n_init=20,
         GT_prior_use = GT_prior[:, order[:n_donor], :]
         modelCA = Vireo(n_var=n_var, n_cell=n_cell, n_donor=n_donor, learn_GT=False,
                         GT_prob_init=GT_prior_use, **kwargs)
-        modelCA.fit(counts, None, min_iter=20, verbose=False)
+        fit_one(modelCA, min_iter=20)
     elif GT_prior is not None and n_donor > GT_prior.shape[1]:
         GT_prior_use = modelCA.GT_prob.copy()
         idx = optimal_match(GT_prior, GT_prior_use)[1]
@@ -135,7 +163,7 @@ def vireo_wrap(AD, DP, GT_prior=None, n_donor=None, learn_GT=True, n_init=20,
                         ID_prob_init=modelCA.ID_prob[:, order], beta_mu_init=modelCA.beta_mu,
                         beta_sum_init=modelCA.beta_sum, GT_prob_init=GT_prior_use, **kwargs)
         modelCA.set_prior(GT_prior=GT_prior_use)
-        modelCA.fit(counts, None, min_iter=20, verbose=False)
+        fit_one(modelCA, min_iter=20)
 
     print("[vireo] allelic rate mean and concentrations:")
     print(np.round(modelCA.beta_mu, 3))
@@ -146,13 +174,17 @@ def vireo_wrap(AD, DP, GT_prior=None, n_donor=None, learn_GT=True, n_init=20,
     print("\t".join(["donor%d" % x for x in range(len(_donor_cnt))]))
     print("\t".join(["%.0f" % x for x in _donor_cnt]))
 
-    if check_doublet:
+    if check_doublet and shard_cells:
+        from .sharded import predict_doublet_sharded
+        doublet_prob, ID_prob, doublet_LLR = predict_doublet_sharded(modelCA, counts, None)
+    elif check_doublet:
         doublet_prob, ID_prob, doublet_LLR = predict_doublet(modelCA, counts, None)
     else:
         ID_prob = modelCA.ID_prob
         doublet_prob = np.zeros((n_cell, int(n_donor * (n_donor - 1) / 2)))
         doublet_LLR = np.zeros(n_cell)
 
+    _mark("doublet", counts.device)
     theta_shapes = np.append(modelCA.beta_mu * modelCA.beta_sum,
                              (1 - modelCA.beta_mu) * modelCA.beta_sum, axis=0)
 
