@@ -752,7 +752,8 @@ def measure_wrap(torch, dist, vb, rank, world, barrier, counts, w, n_init=8):
     argmax -> final fit of up to 200 iterations -> doublet pass) on the N GPUs, split into its phases."""
     import contextlib
     import io
-    from vireo_b200 import vireo_wrap as vw
+    import importlib
+    vw = importlib.import_module("vireo_b200.vireo_wrap")     # the module (the package re-exports the function by that name)
     K = w["K"]
     kw = dict(n_donor=K, n_init=n_init, random_seed=1)
     if w["mode"] == "gt_given":

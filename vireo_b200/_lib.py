@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvireo_b200.so")
+# VIREO_B200_LIB: another build of the same sources (the sanitizer variants of build.py), never a different backend
+LIB_PATH = os.environ.get("VIREO_B200_LIB") or os.path.join(HERE, "libvireo_b200.so")
 
 VB_I32, VB_I64, VB_F32, VB_F64 = 0, 1, 2, 3
 PH_SNP, PH_THETA, PH_GT, PH_ID, PH_ELBO, PH_LOGLIK, PH_THETA_SUMS = 1, 2, 4, 8, 16, 32, 64

@@ -25,25 +25,32 @@ def nvcc_path():
     raise RuntimeError("nvcc not found: libvireo_b200.so cannot be built")
 
 
-def up_to_date():
-    if not os.path.exists(LIB):
+# sanitizer variants: same sources, one macro (see vb_seg.cu); built on demand, loaded through VIREO_B200_LIB
+VARIANTS = {"plainfill": ["-DVB_SEG_PLAIN_FILL"]}
+
+
+def up_to_date(lib=LIB):
+    if not os.path.exists(lib):
         return False
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
-        return LIB
+def build(force=False, verbose=False, variant=None):
+    lib = LIB if variant is None else LIB.replace(".so", "_%s.so" % variant)
+    if not force and up_to_date(lib):
+        return lib
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", "-shared",
-           "-Xptxas", "-v" if verbose else "-O3", "-o", LIB, *SRC, "-ldl"]
+           *(VARIANTS[variant] if variant else []),
+           "-Xptxas", "-v" if verbose else "-O3", "-o", lib, *SRC, "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed (exit %d):\n%s" % (res.returncode, res.stderr[-4000:]))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=var[0] if var else None))

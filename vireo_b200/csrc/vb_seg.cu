@@ -697,6 +697,22 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
             uint32_t use = 0;                               // how often buffer bi has been filled before
             for (int wd = 0; wd < sv.n_win; ++wd) {
                 if (use > 0) mbar_wait(bars + 8 * (NB + bi), (use - 1) & 1);      // every consumer released the previous fill
+#ifdef VB_SEG_PLAIN_FILL
+                // Sanitizer variant (build.py variant "plainfill"): the same full/empty protocol with the window filled
+                // by ordinary loads and stores of the producer warp instead of cp.async.bulk, so that racecheck --
+                // which follows generic-proxy accesses and mbarrier arrive/wait, but not the completion of
+                // async-proxy bulk copies -- can check the protocol itself.  Results are bit-identical.
+                {
+                    const int64_t r0 = (int64_t)wd * sv.win_rows;
+                    const int64_t rows = sv.n_gather - r0 < sv.win_rows ? sv.n_gather - r0 : sv.win_rows;
+                    const uint32_t n16 = (uint32_t)(rows * ROWB / 16);
+                    const uint4* src = reinterpret_cast<const uint4*>(T + (size_t)r0 * ROWB);
+                    uint4* dst = reinterpret_cast<uint4*>(smem + (size_t)bi * win_bytes);
+                    for (uint32_t e = lane; e < n16; e += 32) dst[e] = __ldg(src + e);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bars + 8 * bi);
+                }
+#else
                 if (lane == 0) {
                     const int64_t r0 = (int64_t)wd * sv.win_rows;
                     const int64_t rows = sv.n_gather - r0 < sv.win_rows ? sv.n_gather - r0 : sv.win_rows;
@@ -710,6 +726,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
                         bulk_g2s(dst + off, src + off, sz, bars + 8 * bi);
                     }
                 }
+#endif
                 __syncwarp();
                 if (++bi == NB) { bi = 0; ++use; }
             }
