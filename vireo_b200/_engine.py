@@ -141,9 +141,10 @@ class StagedCounts:
         return self._h
 
     def close(self):
-        for sh in self._shards.values():
-            sh[0].close()
-        self._shards = {}
+        shards, self._shards = self._shards, {}
+        for sh in shards.values():
+            if sh[0] is not self:                  # on one rank the "shard" is the handle itself
+                sh[0].close()
         self._pool = {}
         if self._h is not None:
             self._finalizer()

@@ -26,7 +26,7 @@ def nvcc_path():
 
 
 # sanitizer variants: same sources, one macro (see vb_seg.cu); built on demand, loaded through VIREO_B200_LIB
-VARIANTS = {"plainfill": ["-DVB_SEG_PLAIN_FILL"]}
+VARIANTS = {"plainfill": ["-DVB_SEG_PLAIN_FILL", "-DVB_SEG_CANARY"], "canary": ["-DVB_SEG_CANARY"]}
 
 
 def up_to_date(lib=LIB):

@@ -697,6 +697,18 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
             uint32_t use = 0;                               // how often buffer bi has been filled before
             for (int wd = 0; wd < sv.n_win; ++wd) {
                 if (use > 0) mbar_wait(bars + 8 * (NB + bi), (use - 1) & 1);      // every consumer released the previous fill
+#ifdef VB_SEG_CANARY
+                // Protocol canary (build.py variants "canary" / "plainfill"): a released buffer is overwritten with NaNs
+                // before it is refilled.  A consumer that read a row before its window's fill had completed, or after it
+                // had released the window, would pick up a NaN, which no later step can remove from its sums -- so
+                // NaN-free, bit-identical results under this build show that no such access happens.
+                {
+                    unsigned long long* dst = reinterpret_cast<unsigned long long*>(smem + (size_t)bi * win_bytes);
+                    for (uint32_t e = lane; e < win_bytes / 8; e += 32) dst[e] = 0x7ff8dead0000beefull;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // before the bulk copies overwrite it
+                    __syncwarp();
+                }
+#endif
 #ifdef VB_SEG_PLAIN_FILL
                 // Sanitizer variant (build.py variant "plainfill"): the same full/empty protocol with the window filled
                 // by ordinary loads and stores of the producer warp instead of cp.async.bulk, so that racecheck --
