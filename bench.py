@@ -718,6 +718,8 @@ def measure_sharded_fit(torch, dist, vb, rank, world, barrier, counts, w, init, 
     torch.cuda.synchronize()
     cut_ms = 1e3 * (time.perf_counter() - t0)
     vb.fit_cell_sharded(fresh(), counts, None, max_iter=3, min_iter=3, verbose=False)     # first use: formats, NCCL
+    import importlib
+    sh = importlib.import_module("vireo_b200.sharded")
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -725,6 +727,13 @@ def measure_sharded_fit(torch, dist, vb, rank, world, barrier, counts, w, init, 
     vb.fit_cell_sharded(ms_, counts, None, **kw)
     torch.cuda.synchronize()
     t_sh = _max_over_ranks(torch, dist, world, time.perf_counter() - t0)
+    barrier()
+    sh.PHASES["on"] = True                       # a second, instrumented run: where the time goes (syncs at every mark)
+    try:
+        vb.fit_cell_sharded(fresh(), counts, None, **kw)
+    finally:
+        sh.PHASES["on"] = False
+    phases = {k: _max_over_ranks(torch, dist, world, v) for k, v in sorted(sh.PHASES["t"].items())}
     barrier()
     out = None
     if rank == 0:
@@ -738,6 +747,7 @@ def measure_sharded_fit(torch, dist, vb, rank, world, barrier, counts, w, init, 
         nz = m1.ID_prob > 1e-300
         out = {"iterations": iters, "n_gpus": world, "sharded_s": t_sh, "one_gpu_s": t_one, "speedup": t_one / t_sh,
                "it_per_s_sharded": iters / t_sh, "it_per_s_one_gpu": iters / t_one, "cut_shard_ms_one_off": cut_ms,
+               "phases_s": phases, "ms_per_iteration_in_loop": 1e3 * phases.get("loop", 0.0) / iters,
                "parity_vs_one_gpu": {
                    "elbo_max_rel_diff": float(np.max(np.abs(ms_.ELBO_ - m1.ELBO_) / np.abs(m1.ELBO_))),
                    "id_prob_max_rel_diff": float(np.max(np.abs(ms_.ID_prob[nz] - m1.ID_prob[nz]) / m1.ID_prob[nz])),

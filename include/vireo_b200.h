@@ -106,7 +106,7 @@ typedef struct vb_ws_sizes {
     int64_t ab;       /* doubles: [B, T, 2*G] digamma differences              */
     int64_t part;     /* doubles: block partial sums                           */
     int64_t scal;     /* doubles: [B, 8] ELBO terms                            */
-    int64_t ctrl;     /* int32:   [B, 4] {done, it_next, last_it, n_decrease}  */
+    int64_t ctrl;     /* int32:   [B, 8] {done, it_next, last_it, n_decrease, 3 tickets of fused tails, -} */
     int64_t rpad;     /* doubles: ID_prob in 128-byte rows [B, n_cell, 16] (gather path, else 0) */
     int64_t heavy;    /* doubles: residual sums [B, max(n_cell, 2 n_var), 16] (gather path, else 0) */
 } vb_ws_sizes;
@@ -268,6 +268,10 @@ int vb_profile_read(double* ms8, int64_t* n8);
 void vb_set_path(int mode);
 /* 1 (default): fits of small matrices replay captured CUDA graphs; 0: plain launches */
 void vb_set_graphs(int on);
+/* 1 (default): inside the fit loops the theta step runs in the tail of the SNP pass and the ELBO / convergence step in
+ * the tail of the cell pass (the CTA that finishes last), three launches per iteration instead of five; 0: stand-alone
+ * k_theta / k_elbo launches.  Same arithmetic in the same order: the results are bit-identical. */
+void vb_set_fuse(int on);
 
 const char* vb_last_error(void);
 /* library build info: "vireo_b200 <version> sm_100a" */

@@ -216,22 +216,63 @@ def test_cfg5_clone_mode_full_restarts_vs_oracle(vb):
     vb.clear_cache()
 
 
-def test_cfg2_full_size_graph_replay_equals_plain_launches(vb):
-    """BASELINE cfg2 (10k x 5k x 4, n_init = 1): small matrices replay captured CUDA graphs of whole iterations; the
-    result must be bit-identical to plain launches, including a fit that stops early and a warm start."""
+def test_cfg2_full_size_graph_replay_and_fused_tails_equal_plain_launches(vb):
+    """BASELINE cfg2 (10k x 5k x 4, n_init = 1): small matrices replay captured CUDA graphs of whole iterations, and
+    inside every fit loop the theta and ELBO steps run in the tails of the two sparse passes.  Both must be bit-identical
+    to five plain launches per iteration, including a fit that stops early and a warm start."""
     from vireo_b200 import _lib
     AD, DP, _, _ = O.synth_counts(10000, 5000, 4, seed=0)
     counts = vb.stage(AD, DP)
     out = {}
-    for graphs in (1, 0):
+    for graphs, fuse in ((1, 1), (0, 1), (1, 0), (0, 0)):
         _lib.load().vb_set_graphs(graphs)
+        _lib.load().vb_set_fuse(fuse)
         np.random.seed(1)
         m = vb.Vireo(n_cell=10000, n_var=5000, n_donor=4)
         m.fit(counts, None, max_iter=20, min_iter=20, delay_fit_theta=3, verbose=False)
         m.fit(counts, None, max_iter=200, min_iter=5, verbose=False)       # warm start, stops on the convergence rule
-        out[graphs] = (m.ELBO_.copy(), m.ID_prob.copy(), m.GT_prob.copy())
+        out[graphs, fuse] = (m.ELBO_.copy(), m.ID_prob.copy(), m.GT_prob.copy())
     _lib.load().vb_set_graphs(1)
-    assert len(out[1][0]) == len(out[0][0]) and len(out[1][0]) > 19
-    for a, b in zip(out[1], out[0]):
-        assert np.array_equal(a, b)
+    _lib.load().vb_set_fuse(1)
+    assert len(out[0, 0][0]) > 19
+    for key in ((1, 1), (0, 1), (1, 0)):
+        assert len(out[key][0]) == len(out[0, 0][0])
+        for a, b in zip(out[key], out[0, 0]):
+            assert np.array_equal(a, b), key
+    vb.clear_cache()
+
+
+def test_fused_tails_equal_plain_launches_on_the_segment_kernels(vb):
+    """The same identity for the window-segment kernels (forced on a K = 16 problem), for the ASE and fixed-GT flag
+    combinations, for the clone model and for the sharded-fit loop on one rank."""
+    from vireo_b200 import _lib
+    AD, DP, _, GT = O.synth_counts(3000, 2000, 16, density=0.05, seed=2)
+    prior = np.full((2000, 16, 3), 0.01)
+    np.put_along_axis(prior, GT[:, :, None], 0.98, axis=2)
+    out = {}
+    try:
+        for path in ("seg", "rows"):
+            for fuse in (1, 0):
+                _lib.set_path(path)
+                _lib.load().vb_set_fuse(fuse)
+                res = []
+                for kw in (dict(), dict(ASE_mode=True), dict(learn_GT=False, GT_prob_init=prior.copy())):
+                    np.random.seed(1)
+                    m = vb.Vireo(n_cell=3000, n_var=2000, n_donor=16, **kw)
+                    m.fit(AD, DP, max_iter=8, min_iter=3, delay_fit_theta=2, verbose=False)
+                    res += [m.ELBO_.copy(), m.ID_prob.copy(), m.GT_prob.copy(), m.beta_mu.copy()]
+                np.random.seed(1)
+                s = vb.Vireo(n_cell=3000, n_var=2000, n_donor=16)
+                vb.fit_cell_sharded(s, AD, DP, max_iter=30, min_iter=3, delay_fit_theta=2, verbose=False, poll_every=4)
+                res += [s.ELBO_.copy(), s.ID_prob.copy(), s.GT_prob.copy()]
+                b = vb.BinomMixtureVB(n_cell=3000, n_var=2000, n_donor=5)
+                b.fit(AD, DP, n_init=3, max_iter=12, max_iter_pre=6, min_iter=2, random_seed=1, verbose=False)
+                res += [b.ELBO_iters.copy(), b.ID_prob.copy()]
+                out[path, fuse] = res
+    finally:
+        _lib.set_path("auto")
+        _lib.load().vb_set_fuse(1)
+    for path in ("seg", "rows"):
+        for a, b in zip(out[path, 1], out[path, 0]):
+            assert a.shape == b.shape and np.array_equal(a, b), path
     vb.clear_cache()

@@ -532,7 +532,7 @@ def test_cell_shards_add_up(vb, cellsnp):
     ON THE DEVICE (vb_counts_slice), run the SNP pass on each, and the sum of the shards' S1 | S2 equals the SNP pass
     over all cells; the shards' cell passes give the rows of the full ID update."""
     from vireo_b200 import _engine, _lib
-    from vireo_b200.sharded import _local_model, cell_shards
+    from vireo_b200.sharded import cell_shards
     AD, DP = cellsnp
     counts = vb.stage(AD, DP)
     np.random.seed(9)
@@ -550,13 +550,13 @@ def test_cell_shards_add_up(vb, cellsnp):
         host = vb.StagedCounts(AD[:, c0:c1], DP[:, c0:c1])
         assert (part.nnz, part.n_cell, part.n_var) == (host.nnz, host.n_cell, host.n_var)
         assert part.binom_const() == host.binom_const()
-        b = _engine.VireoBatch(part, [_local_model(m, c0, c1)])
+        b = _engine.VireoBatch(part, [m], rows=(c0, c1))
         b.run_step(_lib.PH_SNP)
         S_sum = S_sum + b.S12.cpu().numpy()
         b.run_step(_lib.PH_ID)
         ll_parts.append(b.loglik_host()[0].copy())
         id_parts.append(b.id_prob.cpu().numpy().reshape(-1, 4).copy())
-        bh = _engine.VireoBatch(host, [_local_model(m, c0, c1)])
+        bh = _engine.VireoBatch(host, [m], rows=(c0, c1))
         bh.run_step(_lib.PH_SNP)
         assert np.array_equal(bh.S12.cpu().numpy(), b.S12.cpu().numpy())       # device-side cut == host-side cut
     rel_close(S_sum, S_full, _tight(1e-12), "S1 | S2 summed over the shards")

@@ -307,11 +307,17 @@ def _log_prior_pair(prior, device):
     return raw, norm
 
 
+_PIN_LIMIT = int(os.environ.get("VIREO_B200_PIN_LIMIT_MB", "64")) << 20
+
+
 def _to_host(tensor):
     """Device tensor -> numpy array that LIVES in pinned memory: one DMA, no second host copy.  The pinned block
     comes from PyTorch's caching host allocator and returns to it when the array is garbage collected."""
     t = torch()
     n = tensor.numel()
+    if n * tensor.element_size() > _PIN_LIMIT:
+        # page-locking a fresh block costs more than the copy it speeds up; blocks this large are rarely recycled
+        return tensor.cpu().numpy()
     buf = t.empty(max(n, 1), dtype=tensor.dtype, pin_memory=True)
     buf[:n].copy_(tensor.reshape(-1), non_blocking=True)
     t.cuda.current_stream(tensor.device).synchronize()
@@ -360,11 +366,20 @@ def _fp_array(a):
     return (a.shape, a.dtype.str, checksum(a))
 
 
-def _vireo_priors(m0, dev, C_, V, K, G, T):
+def _vireo_priors(m0, dev, C_, V, K, G, T, rows=None):
     """Device-side priors of a Vireo model: logs of the donor and genotype priors (both flavours, see
     ``_log_prior_pair``) and the theta prior.  They are constants of the model like the count matrices, so the
     device copies are re-used while a checksum over the FULL contents of every prior array still matches
-    (an in-place edit such as ``model.GT_prior[i, 0, :] = ...`` is always picked up)."""
+    (an in-place edit such as ``model.GT_prior[i, 0, :] = ...`` is always picked up).
+    ``rows = (c0, c1, n_cell_full)``: the batch covers the cells [c0, c1) of a model over n_cell_full cells (cell-sharded
+    fit): the priors are those of the full model, a per-cell ID prior is sliced on the device."""
+    if rows is not None:
+        c0, c1, C_full = rows
+        out = dict(_vireo_priors(m0, dev, C_full, V, K, G, T))
+        if out["id_rows"] != 1:
+            out["lidp"], out["lidp_kl"] = out["lidp"][c0 * K:c1 * K], out["lidp_kl"][c0 * K:c1 * K]
+            out["id_rows"] = c1 - c0
+        return out
     arrs = (m0.ID_prior, m0.GT_prior, m0.theta_s1_prior, m0.theta_s2_prior)
     key = tuple(id(a) for a in arrs) + (dev, C_, V, K, G, T)
     fp = tuple(_fp_array(a) for a in arrs)
@@ -434,7 +449,9 @@ def _release_ws(counts, key, bufs):
 class VireoBatch:
     """Device state of B Vireo restarts that share shapes, flags and priors."""
 
-    def __init__(self, counts, models):
+    def __init__(self, counts, models, rows=None):
+        """``rows = (c0, c1)``: `counts` holds the cells [c0, c1) of the models' matrices (cell-sharded fit): the batch
+        keeps those rows of ID_prob and of a per-cell ID prior; everything else is the full model's."""
         self.counts = counts
         self.models = list(models)
         m0 = self.models[0]
@@ -442,7 +459,10 @@ class VireoBatch:
         self.dev = dev
         B = len(self.models)
         C_, V, K, G = counts.n_cell, counts.n_var, int(m0.n_donor), int(m0.n_GT)
-        if (m0.n_cell, m0.n_var) != (C_, V):
+        self.rows = None if rows is None else (int(rows[0]), int(rows[1]), int(m0.n_cell))
+        if rows is not None and (B != 1 or rows[1] - rows[0] != C_ or m0.n_var != V):
+            raise ValueError("cell range %r does not match the staged shard (%d cells)" % (rows, C_))
+        if rows is None and (m0.n_cell, m0.n_var) != (C_, V):
             raise ValueError("model is (%d cells, %d variants) but the count matrices are (%d variants, %d cells)"
                              % (m0.n_cell, m0.n_var, V, C_))
         if G > _lib.MAX_GT or K > _lib.MAX_DONOR:
@@ -468,12 +488,13 @@ class VireoBatch:
         self.id_prob, self.gt_prob = st[:n_id], st[n_id:n_id + n_gt]
         self.beta_mu, self.beta_sum = st[n_id + n_gt:n_id + n_gt + n_th], st[n_id + n_gt + n_th:n_id + n_gt + 2 * n_th]
         for i, m in enumerate(self.models):
-            _upload_into(self.id_prob[i * C_ * K:(i + 1) * C_ * K], m.ID_prob, (C_, K))
+            idp = m.ID_prob if rows is None else np.asarray(m.ID_prob)[rows[0]:rows[1]]
+            _upload_into(self.id_prob[i * C_ * K:(i + 1) * C_ * K], idp, (C_, K))
             _upload_into(self.gt_prob[i * V * K * G:(i + 1) * V * K * G], m.GT_prob, (V, K, G))
             _upload_into(self.beta_mu[i * T * G:(i + 1) * T * G], m.beta_mu, (T, G))
             _upload_into(self.beta_sum[i * T * G:(i + 1) * T * G], m.beta_sum, (T, G))
 
-        pri = _vireo_priors(m0, dev, C_, V, K, G, T)
+        pri = _vireo_priors(m0, dev, C_, V, K, G, T, self.rows)
         self.id_rows, self.thp_rows = pri["id_rows"], pri["thp_rows"]
         self.lidp, self.lidp_kl, self.lgtp, self.lgtp_kl = pri["lidp"], pri["lidp_kl"], pri["lgtp"], pri["lgtp_kl"]
         self.s1p, self.s2p = pri["s1p"], pri["s2p"]

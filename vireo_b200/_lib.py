@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("VIREO_B200_LIB") or os.path.join(HERE, "libvireo_b200
 VB_I32, VB_I64, VB_F32, VB_F64 = 0, 1, 2, 3
 PH_SNP, PH_THETA, PH_GT, PH_ID, PH_ELBO, PH_LOGLIK, PH_THETA_SUMS = 1, 2, 4, 8, 16, 32, 64
 MAX_GT, MAX_DONOR = 8, 256
-CTRL_N, SCAL_N = 4, 8
+CTRL_N, SCAL_N = 8, 8
 
 c_dp = C.c_void_p  # device pointer
 
@@ -88,6 +88,7 @@ SIGNATURES = {
     "vb_vireo_gt_sharded": (C.c_int, [C.c_void_p, C.POINTER(VireoArgs), C.c_void_p, c_dp, C.c_void_p]),
     "vb_set_path": (None, [C.c_int]),
     "vb_set_graphs": (None, [C.c_int]),
+    "vb_set_fuse": (None, [C.c_int]),
     "vb_launch_counts": (None, [C.POINTER(C.c_int64)]),
     "vb_profile_enable": (None, [C.c_int]),
     "vb_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -16,7 +16,7 @@
 #define VB_THREADS 256
 #define VB_WARPS (VB_THREADS / 32)
 #define VB_FULL 0xffffffffu
-#define VB_CTRL_N 4   // {done, it_next, last_it, n_decrease}
+#define VB_CTRL_N 8   // {done, it_next, last_it, n_decrease, ticket of the SNP pass, of the cell pass, of k_theta_sums, -}
 #define VB_SCAL_N 8   // {ELBO, LB_p, KL_ID, KL_GT, KL_theta, -, -, -}
 
 // ----------------------------------------------------------------------------------------------
@@ -165,6 +165,10 @@ struct EmP {
     int64_t part_stride;
     int off_theta, off_klgt, off_cell, off_klth;
     int n_snpblk, n_elemblk, n_cellblk, n_klth;
+    // tails of the sparse passes (vb_tail.cuh): 0 none, 1 theta after the SNP pass + ELBO after the cell pass (fit
+    // loop), 2 exchange packing after the cell pass (cell-sharded fit; xs = two doubles behind S1 | S2)
+    int fuse;
+    double* xs;
 };
 
 // ----------------------------------------------------------------------------------------------

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "vb_common.cuh"
+#include "vb_tail.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // launch accounting: every kernel launch of the EM path goes through VB_LAUNCH, which counts it and,
@@ -222,6 +223,7 @@ k_cell(const CountsView m, const EmP p, const int mode, const int k_off) {
         out[0] = t0;
         out[1] = t1;
     }
+    cell_pass_tail(p, b);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -234,7 +236,10 @@ k_snp(const CountsView m, const EmP p, const int theta_mode) {
     const int b = blockIdx.y;
     if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
     const bool do_theta = !p.bmm && vb_theta_on(p, b, theta_mode);
-    if (!p.bmm && !do_theta && !p.learn_gt && theta_mode == 2) return;   // nothing consumes S1/S2 this iteration
+    if (!p.bmm && !do_theta && !p.learn_gt && theta_mode == 2) {         // nothing consumes S1/S2 this iteration
+        snp_pass_tail(p, b, theta_mode, false);
+        return;
+    }
     constexpr int NPW = 32 / KT;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int sub = lane / KT, kl = lane % KT;
@@ -333,7 +338,7 @@ k_snp(const CountsView m, const EmP p, const int theta_mode) {
                 }
         }
     }
-    if (!do_theta || p.ase) return;
+    if (!do_theta || p.ase) { snp_pass_tail(p, b, theta_mode, false); return; }
     __shared__ double sh[VB_WARPS][2 * VB_MAX_GT];
 #pragma unroll
     for (int g = 0; g < VB_MAX_GT; ++g) {
@@ -349,30 +354,76 @@ k_snp(const CountsView m, const EmP p, const int theta_mode) {
         if (g < G)
             for (int w = 0; w < VB_WARPS; ++w) t += sh[w][threadIdx.x];
         p.part[(size_t)b * p.part_stride + p.off_theta + (size_t)blockIdx.x * 2 * VB_MAX_GT + threadIdx.x] = t;
-    }
+    }    snp_pass_tail(p, b, theta_mode, true);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Row kernels for few donors (K <= 8), one warp per row, one LANE per nnz: every lane gathers the whole K-wide table
-// row(s) of its own nnz and keeps K private accumulators, so 32 nnz are in flight per step instead of 32/KT -- the
-// passes of small matrices are chains of dependent L2 latencies, and this shortens the chain four- to eightfold.
-// The K accumulators are folded across the warp once per row (xor butterfly: every lane ends with the same bits).
+// row of its own nnz and keeps K private accumulators.  Small matrices are served by these: their passes are
+// instruction- and latency-bound (measured at 10k x 5k x 4 on the KT-lanes-per-nnz kernels: 11.5 warp instructions
+// per nnz, issue slots 50% busy, the rest dependent L2 latencies), so
+//   * a lane handles U records per round: the U record loads are issued together, then the U table-row gathers
+//     (one 16-byte load per two columns), then the FMAs -- two L2 latencies per round instead of two per record;
+//   * a record gathers ONE row in the cell pass (most reads are pure reference or pure alternative; the second
+//     allele of a heterozygous read takes a rare extra load);
+//   * counts become doubles by the 2^52 trick (no conversion pipe), FMAs are unconditional (0 * finite);
+//   * the K accumulators are folded across the warp by a reduce-scatter butterfly: every exchange halves the columns
+//     a lane carries, K - 1 + log2(32 / K) shuffles instead of 5 K; lanes [c * 32 / KP, (c + 1) * 32 / KP) end up
+//     holding the total of column c (all with the same bits), and the softmax runs across those lane groups.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cnt2dbl(uint32_t c) { return __hiloint2double(0x43300000, (int)c) - 4503599627370496.0; }
+
 template <int KP>
-__device__ __forceinline__ void warp_fold(double (&a)[KP]) {
+__device__ __forceinline__ double fold_scatter(double (&a)[KP], int lane) {
+    // after the step with distance `off` a lane keeps the half of its columns selected by that bit of its id
+    int n = KP;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
+    for (int off = 16; off >= 32 / KP; off >>= 1) {
+        n >>= 1;
+        const bool up = (lane & off) != 0;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) a[k] += __shfl_xor_sync(VB_FULL, a[k], off);
+        for (int k = 0; k < KP / 2; ++k) {
+            if (k < n) {
+                const double send = up ? a[k] : a[k + n];
+                const double keep = up ? a[k + n] : a[k];
+                a[k] = keep + __shfl_xor_sync(VB_FULL, send, off);
+            }
+        }
+    }
+    double t = a[0];
+#pragma unroll
+    for (int off = 32 / KP / 2; off > 0; off >>= 1) t += __shfl_xor_sync(VB_FULL, t, off);
+    return t;      // total of column lane / (32 / KP)
 }
 
-template <int KP, bool WIDE>
-__global__ void __launch_bounds__(VB_THREADS)
+
+// the K (<= KP) doubles of a table row; 16-byte loads when the row is exactly KP wide (rows are then 16-byte aligned)
+template <int KP>
+__device__ __forceinline__ void load_row(const double* __restrict__ row, int K, bool on, double (&w)[KP]) {
+    if (K == KP) {
+        const double2* __restrict__ r2 = reinterpret_cast<const double2*>(row);
+#pragma unroll
+        for (int k = 0; k < KP / 2; ++k) {
+            double2 v = make_double2(0.0, 0.0);
+            if (on) v = __ldg(r2 + k);
+            w[2 * k] = v.x; w[2 * k + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) w[k] = (on && k < K) ? __ldg(row + k) : 0.0;
+    }
+}
+
+// U = records per lane and round (more in flight per lane against fewer warps per SM: more registers)
+template <int KP, bool WIDE, int U>
+__global__ void __launch_bounds__(VB_THREADS, U * KP <= 8 ? 4 : 2)
 k_cell_lane(const CountsView m, const EmP p, const int mode) {
+    constexpr int GW = 32 / KP;                            // lanes per column after the fold
     const int b = blockIdx.y;
     if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int K = p.K;
+    const int col = lane / GW;                             // the column this lane owns after the fold
     const double* __restrict__ Wt = p.Wt + (size_t)b * p.V * 2 * K;
     double* __restrict__ R = p.R ? p.R + (size_t)b * p.C * K : nullptr;
     double* __restrict__ LL = p.ll + (size_t)b * p.C * K;
@@ -383,50 +434,58 @@ k_cell_lane(const CountsView m, const EmP p, const int mode) {
 #pragma unroll
         for (int k = 0; k < KP; ++k) acc[k] = 0.0;
         const int64_t p1 = m.cell_ptr[j + 1];
-        for (int64_t q = m.cell_ptr[j] + lane; q < p1; q += 32) {
-            int av, bv;
-            decode<WIDE>(__ldg(m.cell_cnt + q), WIDE ? __ldg(m.cell_dp + q) : 0u, av, bv);
-            const double* __restrict__ row = Wt + (size_t)__ldg(m.cell_idx + q) * 2 * K;
+        for (int64_t q0 = m.cell_ptr[j] + lane; q0 < p1; q0 += 32 * U) {
+            int av[U], bv[U], ii[U];
 #pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                if (k < K) {
-                    if (bv) acc[k] = axpy_count(bv, __ldg(row + k), acc[k]);
-                    if (av) acc[k] = axpy_count(av, __ldg(row + K + k), acc[k]);
+            for (int u = 0; u < U; ++u) {
+                const int64_t q = q0 + 32 * u;
+                const bool ok = q < p1;
+                const uint32_t c = ok ? __ldg(m.cell_cnt + q) : 0u;
+                const uint32_t d = (WIDE && ok) ? __ldg(m.cell_dp + q) : 0u;
+                ii[u] = ok ? __ldg(m.cell_idx + q) : 0;
+                decode<WIDE>(c, d, av[u], bv[u]);
+            }
+            double w[U][KP];
+#pragma unroll
+            for (int u = 0; u < U; ++u)       // alternative-allele row when the read has alternative counts, else reference
+                load_row<KP>(Wt + (size_t)ii[u] * 2 * K + (av[u] ? K : 0), K, (av[u] | bv[u]) != 0, w[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double c1 = cnt2dbl((uint32_t)(av[u] ? av[u] : bv[u]));
+#pragma unroll
+                for (int k = 0; k < KP; ++k) acc[k] = fma(c1, w[u][k], acc[k]);
+                if (av[u] && bv[u]) {         // both alleles seen: add the reference row as well
+                    double w2[KP];
+                    load_row<KP>(Wt + (size_t)ii[u] * 2 * K, K, true, w2);
+                    const double c2 = cnt2dbl((uint32_t)bv[u]);
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) acc[k] = fma(c2, w2[k], acc[k]);
                 }
             }
         }
-        warp_fold<KP>(acc);
+        const double ll = fold_scatter<KP>(acc, lane);     // logLik_ID[j, col]
         const size_t prow = (size_t)(p.id_rows == 1 ? 0 : j) * K;
-        double pr[KP];
+        const bool live = col < K;
+        double pr;
         if (mode == 0) {
-            double mx = -INFINITY;
+            const double lg = live ? ll + p.lidp[prow + col] : -INFINITY;
+            double mx = lg;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                pr[k] = k < K ? acc[k] + p.lidp[prow + k] : -INFINITY;
-                mx = fmax(mx, pr[k]);
-            }
-            double z = 0.0;
+            for (int off = GW; off < 32; off <<= 1) mx = fmax(mx, __shfl_xor_sync(VB_FULL, mx, off));
+            const double e = live ? exp(lg - mx) : 0.0;
+            double z = e;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                pr[k] = k < K ? exp(pr[k] - mx) : 0.0;
-                z += pr[k];
-            }
-#pragma unroll
-            for (int k = 0; k < KP; ++k) pr[k] = pr[k] / z;
+            for (int off = GW; off < 32; off <<= 1) z += __shfl_xor_sync(VB_FULL, z, off);
+            pr = e / z;
         } else {
-#pragma unroll
-            for (int k = 0; k < KP; ++k) pr[k] = k < K ? R[(size_t)j * K + k] : 0.0;
+            pr = live ? R[(size_t)j * K + col] : 0.0;
         }
-        // lane k owns column k of the outputs and of the ELBO partial sums
-#pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            if (k == lane && k < K) {
-                const size_t e = (size_t)j * K + k;
-                LL[e] = acc[k];
-                if (mode == 0) R[e] = pr[k];
-                lbp += acc[k] * pr[k];
-                if (pr[k] > 0.0) klid += pr[k] * (log(pr[k]) - p.lidp_kl[prow + k]);
-            }
+        if (live && (lane % GW) == 0) {
+            const size_t e = (size_t)j * K + col;
+            LL[e] = ll;
+            if (mode == 0) R[e] = pr;
+            lbp += ll * pr;
+            if (pr > 0.0) klid += pr * (log(pr) - p.lidp_kl[prow + col]);
         }
     }
     __shared__ double sh[VB_WARPS];
@@ -437,17 +496,23 @@ k_cell_lane(const CountsView m, const EmP p, const int mode) {
         out[0] = t0;
         out[1] = t1;
     }
+    cell_pass_tail(p, b);
 }
 
-template <int KP, bool WIDE>
-__global__ void __launch_bounds__(VB_THREADS)
+template <int KP, bool WIDE, int U>
+__global__ void __launch_bounds__(VB_THREADS, U * KP <= 8 ? 4 : 2)
 k_snp_lane(const CountsView m, const EmP p, const int theta_mode) {
+    constexpr int GW = 32 / KP;
     const int b = blockIdx.y;
     if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
     const bool do_theta = !p.bmm && vb_theta_on(p, b, theta_mode);
-    if (!p.bmm && !do_theta && !p.learn_gt && theta_mode == 2) return;   // nothing consumes S1/S2 this iteration
+    if (!p.bmm && !do_theta && !p.learn_gt && theta_mode == 2) {         // nothing consumes S1/S2 this iteration
+        snp_pass_tail(p, b, theta_mode, false);
+        return;
+    }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int K = p.K, G = p.G;
+    const int col = lane / GW;
     const double* __restrict__ R = p.R + (size_t)b * p.C * K;
     const double* __restrict__ GT = p.GT ? p.GT + (size_t)b * p.V * K * G : nullptr;
     double* __restrict__ S1 = p.S1 + (size_t)b * p.V * K;
@@ -461,36 +526,40 @@ k_snp_lane(const CountsView m, const EmP p, const int theta_mode) {
 #pragma unroll
         for (int k = 0; k < KP; ++k) a1[k] = a2[k] = 0.0;
         const int64_t p1 = m.snp_ptr[i + 1];
-        for (int64_t q = m.snp_ptr[i] + lane; q < p1; q += 32) {
-            int av, bv;
-            decode<WIDE>(__ldg(m.snp_cnt + q), WIDE ? __ldg(m.snp_dp + q) : 0u, av, bv);
-            const double* __restrict__ row = R + (size_t)__ldg(m.snp_idx + q) * K;
+        for (int64_t q0 = m.snp_ptr[i] + lane; q0 < p1; q0 += 32 * U) {
+            int av[U], bv[U], jj[U];
 #pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                if (k < K) {
-                    const double w = __ldg(row + k);
-                    if (av) a1[k] = axpy_count(av, w, a1[k]);
-                    if (bv) a2[k] = axpy_count(bv, w, a2[k]);
-                }
+            for (int u = 0; u < U; ++u) {
+                const int64_t q = q0 + 32 * u;
+                const bool ok = q < p1;
+                const uint32_t c = ok ? __ldg(m.snp_cnt + q) : 0u;
+                const uint32_t d = (WIDE && ok) ? __ldg(m.snp_dp + q) : 0u;
+                jj[u] = ok ? __ldg(m.snp_idx + q) : 0;
+                decode<WIDE>(c, d, av[u], bv[u]);
+            }
+            double w[U][KP];
+#pragma unroll
+            for (int u = 0; u < U; ++u) load_row<KP>(R + (size_t)jj[u] * K, K, (av[u] | bv[u]) != 0, w[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double ca = cnt2dbl((uint32_t)av[u]), cb = cnt2dbl((uint32_t)bv[u]);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) { a1[k] = fma(ca, w[u][k], a1[k]); a2[k] = fma(cb, w[u][k], a2[k]); }
             }
         }
-        warp_fold<KP>(a1);
-        warp_fold<KP>(a2);
+        const double s1 = fold_scatter<KP>(a1, lane), s2 = fold_scatter<KP>(a2, lane);
+        if (col < K && (lane % GW) == 0) {
+            const size_t e = (size_t)i * K + col;
+            S1[e] = s1;
+            S2[e] = s2;
+            if (do_theta) {
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            if (k == lane && k < K) {
-                const size_t e = (size_t)i * K + k;
-                S1[e] = a1[k];
-                S2[e] = a2[k];
-                if (do_theta) {
-#pragma unroll
-                    for (int g = 0; g < VB_MAX_GT; ++g)
-                        if (g < G) {
-                            const double gt = GT[e * G + g];
-                            t1[g] += a1[k] * gt;
-                            t2[g] += a2[k] * gt;
-                        }
-                }
+                for (int g = 0; g < VB_MAX_GT; ++g)
+                    if (g < G) {
+                        const double gt = GT[e * G + g];
+                        t1[g] += s1 * gt;
+                        t2[g] += s2 * gt;
+                    }
             }
         }
         if (do_theta && p.ase) {
@@ -505,7 +574,7 @@ k_snp_lane(const CountsView m, const EmP p, const int theta_mode) {
                 }
         }
     }
-    if (!do_theta || p.ase) return;
+    if (!do_theta || p.ase) { snp_pass_tail(p, b, theta_mode, false); return; }
     __shared__ double sh[VB_WARPS][2 * VB_MAX_GT];
 #pragma unroll
     for (int g = 0; g < VB_MAX_GT; ++g) {
@@ -521,74 +590,16 @@ k_snp_lane(const CountsView m, const EmP p, const int theta_mode) {
         if (g < G)
             for (int w = 0; w < VB_WARPS; ++w) t += sh[w][threadIdx.x];
         p.part[(size_t)b * p.part_stride + p.off_theta + (size_t)blockIdx.x * 2 * VB_MAX_GT + threadIdx.x] = t;
-    }
+    }    snp_pass_tail(p, b, theta_mode, true);
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_theta (shared theta, T = 1): one CTA per restart
 // ---------------------------------------------------------------------------------------------
-struct ThetaOut { double A, B, kl; };
-
-__device__ __forceinline__ ThetaOut theta_finish(const EmP& p, bool do_theta, double sum1, double sum2, double q1,
-                                                 double q2, double* mu_io, double* sum_io) {
-    double mu = *mu_io, sm = *sum_io;
-    if (do_theta) {
-        const double s1 = q1 + sum1, s2 = q2 + sum2;          // vireo_model.py:173-181
-        mu = s1 / (s1 + s2);                                  // :183
-        if (!p.fix_beta_sum) sm = s1 + s2;                    // :184-185
-        *mu_io = mu;
-        *sum_io = sm;
-    }
-    const double e1 = mu * sm, e2 = (1.0 - mu) * sm;          // theta_s1 / theta_s2 (:139-147)
-    const double es = e1 + e2;
-    const double psi1 = vb_digamma(e1), psi2 = vb_digamma(e2), psis = vb_digamma(es);
-    ThetaOut o;
-    o.A = psi1 - psis;
-    o.B = psi2 - psis;
-    o.kl = vb_beta_kl(e1, e2, q1, q2, psi1, psi2, psis);
-    return o;
-}
-
 __global__ void __launch_bounds__(2 * VB_MAX_GT * 32) k_theta(const EmP p, const int theta_mode) {
     const int b = blockIdx.y;
     if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
-    const bool do_theta = vb_theta_on(p, b, theta_mode);
-    const int G = p.G;
-    __shared__ double tot[2 * VB_MAX_GT];
-    __shared__ double kls[VB_MAX_GT];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;    // warp w sums slot w of every block partial
-    if (do_theta) {
-        const double* src = p.part + (size_t)b * p.part_stride + p.off_theta + w;
-        double t = 0.0;
-        for (int blk = lane; blk < p.n_snpblk; blk += 32) t += src[(size_t)blk * 2 * VB_MAX_GT];
-        t = warp_sum(t);
-        if (lane == 0) tot[w] = t;
-    }
-    __syncthreads();
-    if (threadIdx.x < G) {
-        const int g = threadIdx.x;
-        ThetaOut o = theta_finish(p, do_theta, tot[g], tot[VB_MAX_GT + g], p.s1p[g], p.s2p[g],
-                                  p.mu + (size_t)b * G + g, p.sum + (size_t)b * G + g);
-        double* ab = p.ab + (size_t)b * 2 * G;
-        ab[g] = o.A;
-        ab[G + g] = o.B;
-        kls[g] = o.kl;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int g = 0; g < G; ++g) t += kls[g];
-        p.part[(size_t)b * p.part_stride + p.off_klth] = t;
-        if (p.tiled == 3) {
-            // fixed-point tables: every table entry is a convex combination of the A_g (or of the B_g), so
-            // |W| <= max_g max(|A_g|, |B_g|) < 2^e and -W * 2^(32-e) fits an unsigned 32-bit value
-            const double* ab = p.ab + (size_t)b * 2 * G;
-            double mx = 0.0;
-            for (int g = 0; g < 2 * G; ++g) mx = fmax(mx, fabs(ab[g]));
-            const int e = (mx > 0.0 && mx < 1e300) ? ilogb(mx) + 1 : 0;
-            p.qscale[b] = ldexp(1.0, 32 - e);
-        }
-    }
+    theta_block(p, b, theta_mode, p.n_snpblk);
 }
 
 // allele-specific mode: theta per SNP; raw sums arrive in the ab rows (see k_snp)
@@ -625,7 +636,7 @@ __global__ void __launch_bounds__(VB_THREADS) k_theta_ase(const EmP p, const int
 // recomputed from S1/S2 -- for callers that reduce S1/S2 across devices after the SNP pass (cell-sharded fit) and
 // therefore cannot use the sums the SNP pass folds into its epilogue.  Same output layout as k_snp.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(VB_THREADS) k_theta_sums(const EmP p) {
+__global__ void __launch_bounds__(VB_THREADS) k_theta_sums(const EmP p, const int tail, const int first) {
     const int b = blockIdx.y;
     if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
     const int K = p.K, G = p.G;
@@ -678,6 +689,16 @@ __global__ void __launch_bounds__(VB_THREADS) k_theta_sums(const EmP p) {
         if (g < G)
             for (int w = 0; w < VB_WARPS; ++w) t += sh[w][threadIdx.x];
         p.part[(size_t)b * p.part_stride + p.off_theta + (size_t)blockIdx.x * 2 * VB_MAX_GT + threadIdx.x] = t;
+    }
+    // cell-sharded fit: the CTA that finishes last closes the previous iteration (ELBO + convergence rule from the
+    // exchanged cell terms) and, unless that ended the fit, finishes theta -- instead of two launches of their own
+    if (tail && vb_last_cta(p.ctrl + b * VB_CTRL_N + 6)) {
+        if (!first) {
+            elbo_block(p, b, 1, p.xs);
+            __syncthreads();
+            if (p.ctrl[b * VB_CTRL_N]) return;
+        }
+        theta_block(p, b, 2, (int)gridDim.x);
     }
 }
 
@@ -825,54 +846,17 @@ __global__ void __launch_bounds__(VB_THREADS) k_log_prior(const double* __restri
 // ---------------------------------------------------------------------------------------------
 // k_elbo: final sums + the convergence rule.  advance = 1 inside the fit loop.
 // ---------------------------------------------------------------------------------------------
-// cell_terms != nullptr (cell-sharded fit): {LB_p, KL_ID} already summed over the blocks and over the ranks
 __global__ void __launch_bounds__(128) k_elbo(const EmP p, const int advance, const double* __restrict__ cell_terms) {
     const int b = blockIdx.y;
-    int* ctrl = p.ctrl + b * VB_CTRL_N;
-    if (advance && ctrl[0]) return;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const double* part = p.part + (size_t)b * p.part_stride;
-    __shared__ double tot[4];
-    double t = 0.0;
-    if (w == 0) { if (cell_terms) { if (lane == 0) t = cell_terms[0]; } else for (int i = lane; i < p.n_cellblk; i += 32) t += part[p.off_cell + 2 * i]; }
-    else if (w == 1) { if (cell_terms) { if (lane == 0) t = cell_terms[1]; } else for (int i = lane; i < p.n_cellblk; i += 32) t += part[p.off_cell + 2 * i + 1]; }
-    else if (w == 2) { if (!p.bmm) for (int i = lane; i < p.n_elemblk; i += 32) t += part[p.off_klgt + i]; }
-    else for (int i = lane; i < p.n_klth; i += 32) t += part[p.off_klth + i];
-    t = warp_sum(t);
-    if (lane == 0) tot[w] = t;
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    const double E = tot[0] - tot[1] - tot[2] - tot[3];          // LB_p - KL_ID - KL_GT - KL_theta (:248)
-    double* sc = p.scal + (size_t)b * VB_SCAL_N;
-    sc[0] = E; sc[1] = tot[0]; sc[2] = tot[1]; sc[3] = tot[2]; sc[4] = tot[3];
-    if (!advance) return;
-    const int it = ctrl[1];
-    double* elbo = p.elbo + (size_t)b * p.max_iter;
-    elbo[it] = E;
-    bool brk = false;
-    if (it > p.min_iter) {                                       // strict, as the reference (:266)
-        const double prev = elbo[it - 1];
-        const bool dec = p.bmm ? (E - prev < -1e-6)              // bmm_model.py:191
-                               : (E < prev - 1e-6);              // vireo_model.py:267
-        if (dec) ctrl[3] += 1;                                   // reference only warns
-        else if (it == p.max_iter - 1) { /* "did not converge" warning, replayed on the host */ }
-        else if (E - prev < p.eps) brk = true;                   // :273
-    }
-    ctrl[2] = it;                                                // the reference returns ELBO[:it]
-    if (brk || it + 1 >= p.max_iter) ctrl[0] = 1;
-    else ctrl[1] = it + 1;
+    if (advance && p.ctrl[b * VB_CTRL_N]) return;
+    elbo_block(p, b, advance, cell_terms);
 }
 
 // cell-sharded fit: the block partials {LB_p, KL_ID} of the local cell pass -> two doubles behind S1 | S2 in the
 // exchange buffer (summed over the ranks by the next iteration's all-reduce)
 __global__ void __launch_bounds__(64) k_xchg_pack(const EmP p, double* __restrict__ out2) {
     if (p.ctrl && p.ctrl[0]) return;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const double* part = p.part;
-    double t = 0.0;
-    for (int i = lane; i < p.n_cellblk; i += 32) t += part[p.off_cell + 2 * i + w];
-    t = warp_sum(t);
-    if (lane == 0) out2[w] = t;
+    xchg_pack_block(p, out2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1022,13 +1006,18 @@ static bool tile_for(int K, int& KT, int& KR) {
         }                                                                         \
     } while (0)
 
-// lane-per-nnz row kernels serve K <= 8 when the rows are long enough to fill the lanes for a few steps (measured
-// at 10k x 5k x 4: SNP rows of ~200 nnz 28.7 -> 24.7 us, cell rows of ~100 nnz 25.9 -> 30.8 us);
-// VIREO_B200_ROWS_LANE=0 keeps the KT-lanes-per-nnz kernels, =2 forces the lane kernels
+// lane-per-nnz row kernels serve every K <= 8 (VIREO_B200_ROWS_LANE=0 keeps the KT-lanes-per-nnz kernels; =1 the
+// round-1 rule: only rows of >= 160 nnz on average)
 static bool rows_lane_ok(int K, int64_t nnz, int64_t n_row) {
-    static const int mode = getenv("VIREO_B200_ROWS_LANE") ? atoi(getenv("VIREO_B200_ROWS_LANE")) : 1;
+    static const int mode = getenv("VIREO_B200_ROWS_LANE") ? atoi(getenv("VIREO_B200_ROWS_LANE")) : 2;
     if (mode == 0 || K > 8) return false;
     return mode == 2 || nnz >= 160 * (n_row > 0 ? n_row : 1);
+}
+
+// VIREO_B200_LANE_DEEP=0: half the records per lane and round, twice the warps per SM
+static bool lane_deep() {
+    static const bool on = !(getenv("VIREO_B200_LANE_DEEP") && atoi(getenv("VIREO_B200_LANE_DEEP")) == 0);
+    return on;
 }
 
 static int launch_cell(const vb_counts* m, const EmP& p, int mode, cudaStream_t st) {
@@ -1038,9 +1027,15 @@ static int launch_cell(const vb_counts* m, const EmP& p, int mode, cudaStream_t 
     const CountsView v = view_of(m);
     const dim3 grid(m->grid_cell, p.B);
     if (rows_lane_ok(p.K, m->N, m->C)) {
+        const bool deep = lane_deep();
         VB_LAUNCH(3, st, {
-            if (p.K <= 4) { if (m->wide) k_cell_lane<4, true><<<grid, VB_THREADS, 0, st>>>(v, p, mode); else k_cell_lane<4, false><<<grid, VB_THREADS, 0, st>>>(v, p, mode); }
-            else { if (m->wide) k_cell_lane<8, true><<<grid, VB_THREADS, 0, st>>>(v, p, mode); else k_cell_lane<8, false><<<grid, VB_THREADS, 0, st>>>(v, p, mode); }
+            if (p.K <= 4) {
+                if (m->wide) { if (deep) k_cell_lane<4, true, 4><<<grid, VB_THREADS, 0, st>>>(v, p, mode); else k_cell_lane<4, true, 2><<<grid, VB_THREADS, 0, st>>>(v, p, mode); }
+                else { if (deep) k_cell_lane<4, false, 4><<<grid, VB_THREADS, 0, st>>>(v, p, mode); else k_cell_lane<4, false, 2><<<grid, VB_THREADS, 0, st>>>(v, p, mode); }
+            } else {
+                if (m->wide) { if (deep) k_cell_lane<8, true, 2><<<grid, VB_THREADS, 0, st>>>(v, p, mode); else k_cell_lane<8, true, 1><<<grid, VB_THREADS, 0, st>>>(v, p, mode); }
+                else { if (deep) k_cell_lane<8, false, 2><<<grid, VB_THREADS, 0, st>>>(v, p, mode); else k_cell_lane<8, false, 1><<<grid, VB_THREADS, 0, st>>>(v, p, mode); }
+            }
         });
         VB_CUDA(cudaGetLastError());
         return VB_OK;
@@ -1057,9 +1052,15 @@ static int launch_snp(const vb_counts* m, const EmP& p, int theta_mode, cudaStre
     const CountsView v = view_of(m);
     const dim3 grid(m->grid_snp, p.B);
     if (rows_lane_ok(p.K, m->N, m->V)) {
+        const bool deep = lane_deep();
         VB_LAUNCH(0, st, {
-            if (p.K <= 4) { if (m->wide) k_snp_lane<4, true><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); else k_snp_lane<4, false><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); }
-            else { if (m->wide) k_snp_lane<8, true><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); else k_snp_lane<8, false><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); }
+            if (p.K <= 4) {
+                if (m->wide) { if (deep) k_snp_lane<4, true, 4><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); else k_snp_lane<4, true, 2><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); }
+                else { if (deep) k_snp_lane<4, false, 4><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); else k_snp_lane<4, false, 2><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); }
+            } else {
+                if (m->wide) { if (deep) k_snp_lane<8, true, 2><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); else k_snp_lane<8, true, 1><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); }
+                else { if (deep) k_snp_lane<8, false, 2><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); else k_snp_lane<8, false, 1><<<grid, VB_THREADS, 0, st>>>(v, p, theta_mode); }
+            }
         });
         VB_CUDA(cudaGetLastError());
         return VB_OK;
@@ -1075,6 +1076,14 @@ static int launch_snp(const vb_counts* m, const EmP& p, int theta_mode, cudaStre
 // ---------------------------------------------------------------------------------------------
 static int g_path = 0;                       // 0 auto, 1 rows, 3 segments (FP64 tables), 4 segments (fixed-point tables)
 static int g_graphs = 1;
+// theta / ELBO steps run in the tail of the sparse passes inside the fit loops (vb_tail.cuh); VIREO_B200_FUSE=0 keeps
+// the stand-alone k_theta / k_elbo launches (same bits either way)
+static int g_fuse = -1;
+static bool fuse_on() {
+    if (g_fuse < 0) g_fuse = (getenv("VIREO_B200_FUSE") && atoi(getenv("VIREO_B200_FUSE")) == 0) ? 0 : 1;
+    return g_fuse != 0;
+}
+extern "C" void vb_set_fuse(int on) { g_fuse = on != 0; }
 #define VB_SEG_MIN_NNZ (4ll << 20)           // below this the passes are launch/latency bound either way
 
 extern "C" void vb_set_path(int mode) { g_path = (mode == 1 || mode == 3 || mode == 4) ? mode : 0; }
@@ -1302,13 +1311,14 @@ static int vireo_iteration(const vb_counts* m, const EmP& p, int phases, bool in
     if (!in_loop && phases == VB_PH_SNP) return VB_OK;      // S1/S2 only (the caller reduces them across devices)
     EmP q = p;
     if (!in_loop && (phases & VB_PH_THETA_SUMS)) {
-        VB_LAUNCH(0, st, k_theta_sums<<<elem, VB_THREADS, 0, st>>>(p));
+        VB_LAUNCH(0, st, k_theta_sums<<<elem, VB_THREADS, 0, st>>>(p, 0, 0));
         VB_CUDA(cudaGetLastError());
         q.n_snpblk = m->grid_elem;                           // k_theta sums this kernel's block partials
     }
-    // k_theta always runs: the digamma tables and KL_theta depend on the current beta_mu / beta_sum
+    // theta always runs: the digamma tables and KL_theta depend on the current beta_mu / beta_sum
+    // (p.fuse == 1: the SNP pass did it in its tail)
     if (p.ase) VB_LAUNCH(1, st, k_theta_ase<<<elem, VB_THREADS, 0, st>>>(q, theta_mode));
-    else VB_LAUNCH(1, st, k_theta<<<one, 2 * VB_MAX_GT * 32, 0, st>>>(q, theta_mode));
+    else if (p.fuse != 1) VB_LAUNCH(1, st, k_theta<<<one, 2 * VB_MAX_GT * 32, 0, st>>>(q, theta_mode));
     VB_CUDA(cudaGetLastError());
     const int do_gt = in_loop ? p.learn_gt : ((phases & VB_PH_GT) ? 1 : 0);
     VB_LAUNCH(2, st, k_gt<<<elem, VB_THREADS, 0, st>>>(p, do_gt));
@@ -1316,7 +1326,10 @@ static int vireo_iteration(const vb_counts* m, const EmP& p, int phases, bool in
     if (phases & VB_PH_ID) { if ((rc = launch_cell(m, p, 0, st))) return rc; }
     else if (phases & VB_PH_LOGLIK) { if ((rc = launch_cell(m, p, 1, st))) return rc; }
     else if (phases & VB_PH_ELBO) { VB_LAUNCH(6, st, k_terms<<<dim3(p.n_cellblk, p.B), VB_THREADS, 0, st>>>(p)); VB_CUDA(cudaGetLastError()); }
-    if (phases & VB_PH_ELBO) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, in_loop ? 1 : 0, nullptr)); VB_CUDA(cudaGetLastError()); }
+    if ((phases & VB_PH_ELBO) && !(in_loop && p.fuse == 1)) {       // p.fuse == 1: the cell pass closed the iteration in its tail
+        VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, in_loop ? 1 : 0, nullptr));
+        VB_CUDA(cudaGetLastError());
+    }
     return VB_OK;
 }
 
@@ -1330,7 +1343,10 @@ static int bmm_iteration(const vb_counts* m, const EmP& p, int phases, bool in_l
     if (phases & VB_PH_ID) { if ((rc = launch_cell(m, p, 0, st))) return rc; }
     else if (phases & VB_PH_LOGLIK) { if ((rc = launch_cell(m, p, 1, st))) return rc; }
     else if (phases & VB_PH_ELBO) { VB_LAUNCH(6, st, k_terms<<<dim3(p.n_cellblk, p.B), VB_THREADS, 0, st>>>(p)); VB_CUDA(cudaGetLastError()); }
-    if (phases & VB_PH_ELBO) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, in_loop ? 1 : 0, nullptr)); VB_CUDA(cudaGetLastError()); }
+    if ((phases & VB_PH_ELBO) && !(in_loop && p.fuse == 1)) {       // p.fuse == 1: the cell pass closed the iteration in its tail
+        VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, in_loop ? 1 : 0, nullptr));
+        VB_CUDA(cudaGetLastError());
+    }
     return VB_OK;
 }
 
@@ -1420,7 +1436,9 @@ static int graph_for(const vb_counts* m, const EmP& p, int n_iter, GraphEntry** 
     return VB_OK;
 }
 
-static int run_loop(const vb_counts* m, const EmP& p, int poll_every, cudaStream_t st) {
+static int run_loop(const vb_counts* m, const EmP& p0, int poll_every, cudaStream_t st) {
+    EmP p = p0;
+    p.fuse = fuse_on() ? 1 : 0;                 // theta / ELBO in the tails of the sparse passes
     if (p.max_iter < 1) { vb_set_error("max_iter must be >= 1"); return VB_E_ARG; }
     if (!p.elbo) { vb_set_error("elbo output is NULL"); return VB_E_ARG; }
     const int n_ctrl = p.B * VB_CTRL_N;
@@ -1773,21 +1791,29 @@ extern "C" int vb_vireo_fit_sharded(const vb_counts* m, const vb_vireo_args* a, 
     }
     int poll_every = a->poll_every > 0 ? a->poll_every : 16;
     const dim3 one(1, 1), elem(m->grid_elem, 1);
+    const bool fused = fuse_on();
+    p.xs = xs;
+    p.fuse = fused ? 2 : 0;                                   // cell pass packs its two ELBO terms in its tail
     EmP q = p;
     q.n_snpblk = m->grid_elem;                                // k_theta sums the block partials of k_theta_sums
     for (int it = 0; it < p.max_iter; ++it) {
         if ((rc = launch_snp(m, p, 0, st))) return rc;        // local S1 | S2 (theta sums need the reduced S: not here)
         if (c->n_ranks > 1) VB_NCCL(g_nccl.AllReduce(xbuf, xbuf, (size_t)(n_x + 2), NCCL_DOUBLE, NCCL_SUM, c->comm, st));
-        if (it > 0) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, 1, xs)); VB_CUDA(cudaGetLastError()); }
-        VB_LAUNCH(0, st, k_theta_sums<<<elem, VB_THREADS, 0, st>>>(p));
-        VB_CUDA(cudaGetLastError());
-        VB_LAUNCH(1, st, k_theta<<<one, 2 * VB_MAX_GT * 32, 0, st>>>(q, 2));
-        VB_CUDA(cudaGetLastError());
+        if (fused) {
+            // theta sums; the last CTA closes iteration it - 1 (ELBO, convergence rule) and finishes theta
+            VB_LAUNCH(0, st, k_theta_sums<<<elem, VB_THREADS, 0, st>>>(p, 1, it == 0));
+            VB_CUDA(cudaGetLastError());
+        } else {
+            if (it > 0) { VB_LAUNCH(4, st, k_elbo<<<one, 128, 0, st>>>(p, 1, xs)); VB_CUDA(cudaGetLastError()); }
+            VB_LAUNCH(0, st, k_theta_sums<<<elem, VB_THREADS, 0, st>>>(p, 0, 0));
+            VB_CUDA(cudaGetLastError());
+            VB_LAUNCH(1, st, k_theta<<<one, 2 * VB_MAX_GT * 32, 0, st>>>(q, 2));
+            VB_CUDA(cudaGetLastError());
+        }
         VB_LAUNCH(2, st, k_gt<<<elem, VB_THREADS, 0, st>>>(p, p.learn_gt));
         VB_CUDA(cudaGetLastError());
         if ((rc = launch_cell(m, p, 0, st))) return rc;
-        VB_LAUNCH(7, st, k_xchg_pack<<<1, 64, 0, st>>>(p, xs));
-        VB_CUDA(cudaGetLastError());
+        if (!fused) { VB_LAUNCH(7, st, k_xchg_pack<<<1, 64, 0, st>>>(p, xs)); VB_CUDA(cudaGetLastError()); }
         if ((it + 1) % poll_every == 0 && it + 1 < p.max_iter) {
             // the flag read here is the verdict on iteration it - 1: identical on every rank (same reduced numbers)
             bool done;

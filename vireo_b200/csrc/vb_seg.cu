@@ -38,6 +38,7 @@
 
 #include "vb_common.cuh"
 #include "vb_stream.cuh"
+#include "vb_tail.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // build kernels
@@ -658,7 +659,10 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     const int b = blockIdx.y;
     if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
     const bool do_theta = sa.mode == GM_SNP && !p.bmm && vb_theta_on(p, b, sa.theta_mode);
-    if (sa.mode == GM_SNP && !p.bmm && !do_theta && !p.learn_gt && sa.theta_mode == 2) return;   // S1/S2 unused this iteration
+    if (sa.mode == GM_SNP && !p.bmm && !do_theta && !p.learn_gt && sa.theta_mode == 2) {   // S1/S2 unused this iteration
+        snp_pass_tail(p, b, sa.theta_mode, false);
+        return;
+    }
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int NW = sa.nwarps, NB = sa.nb;
@@ -950,6 +954,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
             out[0] = a;
             out[1] = c;
         }
+        if (sa.mode == GM_CELL) cell_pass_tail(p, b);
     } else if (sa.mode == GM_SNP && do_theta && !p.ase) {
 #pragma unroll
         for (int gq = 0; gq < VB_MAX_GT; ++gq) {
@@ -966,6 +971,9 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
                 for (int i = 0; i < nwt; ++i) t += red[i * VB_SG_RED_DOUBLES + threadIdx.x];
             p.part[(size_t)b * p.part_stride + p.off_theta + (size_t)blockIdx.x * 2 * VB_MAX_GT + threadIdx.x] = t;
         }
+        snp_pass_tail(p, b, sa.theta_mode, true);
+    } else if (sa.mode == GM_SNP) {
+        snp_pass_tail(p, b, sa.theta_mode, false);
     }
 }
 

@@ -17,7 +17,6 @@ The convergence rule, the ``ELBO[:it]`` quirk and the binomial constant follow t
 (vireo_model.py:266-276,313); the constant is the single float32 sum over the FULL matrices (every rank has them
 staged), as in the reference.  On a single rank the same library loop runs without the exchange.
 """
-import copy
 import ctypes as C
 
 import numpy as np
@@ -51,33 +50,39 @@ def shard_of(counts):
     return counts._shards[key]
 
 
-def _local_model(model, c0, c1):
-    loc = copy.copy(model)
-    loc.n_cell = int(c1 - c0)
-    loc.ID_prob = np.ascontiguousarray(model.ID_prob[c0:c1])
-    pri = np.asarray(model.ID_prior)
-    loc.ID_prior = pri if (pri.ndim == 1 or pri.shape[0] == 1) else np.ascontiguousarray(pri[c0:c1])
-    return loc
-
-
 def _gather_rows(cm, local, n_cols, bounds, dev):
-    """All-gather of per-rank row blocks [c1 - c0, n_cols] (device tensor `local`) -> host array [n_cell, n_cols]."""
+    """All-gather of per-rank row blocks [c1 - c0, n_cols] (device tensor `local`) -> host array [n_cell, n_cols]:
+    one NCCL all-gather of padded blocks, the blocks are packed on the device, ONE download."""
     t = _engine.torch()
     ws = cm.world
-    per = int(np.max(np.diff(bounds))) * n_cols
-    send = t.zeros(max(per, 1), dtype=t.float64, device="cuda:%d" % dev)
-    send[:local.numel()].copy_(local.reshape(-1))
-    recv = t.empty(max(per, 1) * ws, dtype=t.float64, device="cuda:%d" % dev)
-    _lib.check(_lib.load().vb_comm_allgather(cm.handle, _engine._ptr(send), _engine._ptr(recv), max(per, 1),
-                                             _engine._stream(dev)))
-    host = _engine._to_host(recv)
     if ws == 1:
-        return host[:local.numel()].reshape(-1, n_cols)
-    out = np.empty((int(bounds[-1]), n_cols))
+        return _engine._to_host(local.reshape(-1)).reshape(-1, n_cols)
+    per = max(int(np.max(np.diff(bounds))) * n_cols, 1)
+    send = t.zeros(per, dtype=t.float64, device="cuda:%d" % dev)
+    send[:local.numel()].copy_(local.reshape(-1))
+    recv = t.empty(per * ws, dtype=t.float64, device="cuda:%d" % dev)
+    _lib.check(_lib.load().vb_comm_allgather(cm.handle, _engine._ptr(send), _engine._ptr(recv), per, _engine._stream(dev)))
+    out = t.empty(int(bounds[-1]) * n_cols, dtype=t.float64, device="cuda:%d" % dev)
     for r in range(ws):
         c0, c1 = int(bounds[r]), int(bounds[r + 1])
-        out[c0:c1] = host[r * per:r * per + (c1 - c0) * n_cols].reshape(c1 - c0, n_cols)
-    return out
+        out[c0 * n_cols:c1 * n_cols].copy_(recv[r * per:r * per + (c1 - c0) * n_cols])
+    return _engine._to_host(out).reshape(int(bounds[-1]), n_cols)
+
+
+# phase timing for bench.py (`sharded_fit.phases_s`): off unless PHASES["on"]; every mark synchronises the device
+PHASES = {"on": False, "last": 0.0, "t": {}}
+
+
+def _mark(name, device, reset=False):
+    if PHASES["on"]:
+        import time
+        _engine.torch().cuda.synchronize(device)
+        now = time.perf_counter()
+        if reset:
+            PHASES["t"] = {}
+        else:
+            PHASES["t"][name] = PHASES["t"].get(name, 0.0) + now - PHASES["last"]
+        PHASES["last"] = now
 
 
 def fit_cell_sharded(model, AD, DP=None, max_iter=200, min_iter=5, epsilon_conv=1e-2, delay_fit_theta=0, verbose=True,
@@ -89,16 +94,20 @@ def fit_cell_sharded(model, AD, DP=None, max_iter=200, min_iter=5, epsilon_conv=
     if getattr(model, "ASE_mode", False):
         raise NotImplementedError("cell-sharded fit: ASE mode keeps theta per SNP; use model.fit")
     counts = _engine.stage(AD, DP)
+    _mark("", counts.device, reset=True)
     local, c0, c1, bounds = shard_of(counts)
     dev = counts.device
     cm = comm(dev)
     K, V = int(model.n_donor), int(model.n_var)
-    batch = _engine.VireoBatch(local, [_local_model(model, c0, c1)])
+    _mark("shard_and_comm", dev)
+    batch = _engine.VireoBatch(local, [model], rows=(c0, c1))
     xbuf = t.zeros(2 * V * K + 8, dtype=t.float64, device="cuda:%d" % dev)
     a = batch.args(max_iter, min_iter, epsilon_conv, delay_fit_theta, poll_every)
+    _mark("upload", dev)
     _lib.check(_lib.load().vb_vireo_fit_sharded(local.handle, C.byref(a), cm.handle, _engine._ptr(xbuf),
                                                 _engine._stream(dev)))
     batch.max_iter = max_iter
+    _mark("loop", dev)
     elbo, last = batch.traces()[0]
     _engine.replay_convergence(elbo, last, max_iter, min_iter, epsilon_conv, False, verbose)
 
@@ -112,6 +121,7 @@ def fit_cell_sharded(model, AD, DP=None, max_iter=200, min_iter=5, epsilon_conv=
     batch.close()
     trace = elbo[:last].copy() + counts.binom_const()      # ELBO[:it] (vireo_model.py:276) + the constant (:313)
     model.ELBO_ = np.append(model.ELBO_, trace)
+    _mark("download", dev)
     return trace
 
 
@@ -133,15 +143,13 @@ def predict_doublet_sharded(vobj, AD, DP=None, update_GT=True, update_ID=True, d
         log_prior_both = log_prior_both[c0:c1]
     pr, llr = _engine.doublet_pass(local, np.asarray(vobj.GT_prob, dtype=np.float64), vobj.beta_mu, vobj.beta_sum,
                                    log_prior_both, vobj.ASE_mode, keep_device=True)
-    both = t.cat([pr.view(local.n_cell, K2), llr.view(local.n_cell, 1)], dim=1).contiguous()
-    full = _gather_rows(cm, both, K2 + 1, bounds, dev)
-    prob_both, llr_all = np.ascontiguousarray(full[:, :K2]), np.ascontiguousarray(full[:, K2])
+    prob_both = _gather_rows(cm, pr, K2, bounds, dev)
+    llr_all = _gather_rows(cm, llr, 1, bounds, dev).reshape(-1)
     if update_ID:
         vobj.ID_prob = prob_both[:, :K].copy()
     if update_GT:
         if update_ID:
-            loc = _local_model(vobj, c0, c1)
-            batch = _engine.VireoBatch(local, [loc])
+            batch = _engine.VireoBatch(local, [vobj], rows=(c0, c1))
             xbuf = t.zeros(2 * V * K + 8, dtype=t.float64, device="cuda:%d" % dev)
             a = batch.args()
             _lib.check(_lib.load().vb_vireo_gt_sharded(local.handle, C.byref(a), cm.handle, _engine._ptr(xbuf),
