@@ -994,6 +994,8 @@ static size_t seg_smem(int prec, int nb, int win_rows) {
 }
 
 static bool g_seg_attr_set[64] = {false};     // per device: function attributes belong to the context
+static size_t g_seg_static[64] = {0};         // largest static shared memory of the k_seg instances
+#define VB_SMEM_OPTIN ((size_t)227 * 1024)
 
 // ori 0: cell pass (table = p.Wt / p.Wq), ori 1: SNP pass (table = p.RP / p.RPq)
 // mode GM_PLAIN (ori 0, FP64 tables): `plain` says where the sums of this column chunk go
@@ -1003,16 +1005,29 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
     if (!g.built) { vb_set_error("segment format was not built"); return VB_E_ARG; }
     const int dev_slot = m->device >= 0 && m->device < 64 ? m->device : 0;
     if (!g_seg_attr_set[dev_slot]) {
-        VB_CUDA(cudaFuncSetAttribute(k_seg<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        VB_CUDA(cudaFuncSetAttribute(k_seg<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        VB_CUDA(cudaFuncSetAttribute(k_seg<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        VB_CUDA(cudaFuncSetAttribute(k_seg<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        VB_CUDA(cudaFuncSetAttribute(k_seg<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        // the opt-in limit covers static + dynamic shared memory: the fused tails (vb_tail.cuh) keep a few hundred
+        // bytes of static shared memory in these kernels
+        size_t st_max = 0;
+        int rc_attr = VB_OK;
+        auto opt_in = [&](const void* fn) {
+            cudaFuncAttributes fa;
+            if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess ||
+                cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VB_SMEM_OPTIN - fa.sharedSizeBytes)) != cudaSuccess) {
+                vb_set_error("segment kernel: shared-memory opt-in failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc_attr = VB_E_CUDA;
+                return;
+            }
+            if (fa.sharedSizeBytes > st_max) st_max = fa.sharedSizeBytes;
+        };
+        opt_in((const void*)k_seg<0, 4>); opt_in((const void*)k_seg<1, 4>); opt_in((const void*)k_seg<0, 8>);
+        opt_in((const void*)k_seg<2, 4>); opt_in((const void*)k_seg<1, 8>);
+        if (rc_attr) return rc_attr;
+        g_seg_static[dev_slot] = st_max;
         g_seg_attr_set[dev_slot] = true;
     }
     const int nb = g.nb;
     const size_t smem = seg_smem(prec, nb, g.win_rows);
-    if (smem > 227 * 1024) { vb_set_error("segment kernel: window buffers exceed shared memory"); return VB_E_ARG; }
+    if (smem + g_seg_static[dev_slot] > VB_SMEM_OPTIN) { vb_set_error("segment kernel: window buffers exceed shared memory"); return VB_E_ARG; }
     const SegView sv = view_of_set(g);
     SegArgs sa;
     memset(&sa, 0, sizeof(sa));
