@@ -93,6 +93,13 @@ int64_t vb_counts_info(const vb_counts* m, int what);
 /* message of the failed format build behind vb_counts_info(m, 60) == 2 ("" otherwise) */
 const char* vb_counts_note(const vb_counts* m);
 
+/* Test hook: builds the window-segment format `table_kind` (0 FP64 rows of 16 columns, 1 fixed point, 2 FP64 rows of
+ * 8 columns) if needed and checks it on the host against the staged counts: every (owner, gather row, count) pair of
+ * pass `pass` (0 cell pass, 1 SNP pass) must appear exactly once, either as a record that executes while its table
+ * row is inside the windows the warp holds, or in the residual list.  out4 = {pairs, errors, super-steps, null
+ * slots}.  No reference counterpart (the reference keeps scipy CSC matrices, vireo_model.py:190-196). */
+int vb_seg_verify(vb_counts* m, int table_kind, int pass, int64_t* out4);
+
 /* sum over nnz(DP>0) of float32(min(log C(dp, ad), 700)), accumulated in float64.
  * Replaces np.sum(get_binom_coeff(AD, DP)) (vireoSNP/utils/vireo_base.py:7-22, vireo_model.py:313,
  * bmm_model.py:239).  `scratch` is a device buffer of >= 1024 doubles. */

@@ -200,3 +200,23 @@ def test_host_state_setup_matches_reference_semantics():
     ob = O.bmm_new(6, 4, 2)
     assert np.array_equal(b.ID_prob, ob.ID_prob) and np.array_equal(b.beta_sum, ob.beta_sum)
     assert np.array_equal(b.theta_s1_prior, ob.theta_s1_prior)
+
+
+def test_segment_record_count_codes():
+    """The records of the window-segment format carry a count as the upper 16 bits of the double 2 * count
+    (vb_seg.cu): exact for every count with at most 5 significant bits, refused (residual list) otherwise; those
+    bits share their upper 7 for every count, which is what lets the kernel form a shared-memory address from the
+    whole record with one shift-add.  Fixed-point tables carry the integer count up to 31."""
+    lib = _lib.load()
+    for c in list(range(1, 300)) + [496, 512, 992, 1000, 1 << 20, 31 << 18, (1 << 24) - 1, 1 << 24]:
+        code = lib.vb_host_seg_count_code(c, 0)
+        sig = len(bin(c).rstrip("0")) - 2            # significant bits
+        if sig <= 5 and c < (1 << 24):
+            top16 = int(np.float64(2.0 * c).view(np.uint64) >> np.uint64(48))
+            assert code == top16, (c, hex(code), hex(top16))
+            assert np.uint64(code << 48).view(np.float64) == 2.0 * c
+            assert code >> 9 == 32 and code >> 10 == 16
+        else:
+            assert code == 0xffffffff, c
+        assert lib.vb_host_seg_count_code(c, 1) == (c if c <= 31 else 0xffffffff)
+    assert lib.vb_host_seg_count_code(0, 0) == 0xffffffff

@@ -9,6 +9,7 @@ import contextlib
 import io
 
 import numpy as np
+from scipy.sparse import csc_matrix
 import pytest
 
 from conftest import rel_close
@@ -276,3 +277,44 @@ def test_fused_tails_equal_plain_launches_on_the_segment_kernels(vb):
         for a, b in zip(out[path, 1], out[path, 0]):
             assert a.shape == b.shape and np.array_equal(a, b), path
     vb.clear_cache()
+
+
+@pytest.mark.parametrize("shape", ["poisson", "heavy_tail", "tiny", "big_counts"])
+def test_segment_format_holds_every_pair_exactly_once(vb, shape):
+    """The window-segment formats (vb_seg.cu) re-encode the staged counts as lock-step record streams whose records
+    carry a shared-memory ring row, not a table row.  vb_seg_verify decodes them on the host with the kernel's own rules
+    (windows held at each super-step, ring addressing, count codes) and compares the multiset of (owner, gather row,
+    count) with the staged matrices: every pair exactly once, stream or residual list, for both passes and all three
+    table kinds, on shapes that stress the schedule (empty stretches, very uneven rows, counts without a code)."""
+    import ctypes
+    from vireo_b200 import _lib
+    rng = np.random.default_rng(5)
+    if shape == "poisson":
+        AD, DP, _, _ = O.synth_counts(3000, 2000, 16, density=0.05, seed=2)
+    elif shape == "heavy_tail":           # a few SNPs covered in most cells, most SNPs in a handful; some empty cells
+        C, V = 2500, 1500
+        pv = np.minimum(1.0, 0.6 / (1 + np.arange(V)) ** 0.9 * 20)
+        mask = rng.random((V, C)) < pv[:, None]
+        mask[:, rng.choice(C, 40, replace=False)] = False
+        dp = np.where(mask, rng.integers(1, 6, size=(V, C)), 0)
+        ad = rng.binomial(dp, 0.4)
+        AD, DP = csc_matrix(ad), csc_matrix(dp)
+    elif shape == "tiny":
+        dp = np.zeros((7, 5), dtype=np.int64); dp[0, 0] = 3; dp[6, 4] = 1; dp[3, 2] = 40
+        ad = np.zeros_like(dp); ad[0, 0] = 1; ad[3, 2] = 33
+        AD, DP = csc_matrix(ad), csc_matrix(dp)
+    else:                                 # counts with and without a 5-significant-bit code, and above 65535 (wide storage)
+        C, V = 600, 400
+        mask = rng.random((V, C)) < 0.08
+        dp = np.where(mask, rng.choice([1, 2, 31, 33, 48, 62, 63, 100, 992, 1000, 70000], size=(V, C)), 0)
+        ad = rng.binomial(dp, 0.5)
+        AD, DP = csc_matrix(ad), csc_matrix(dp)
+    counts = vb.stage(AD, DP)
+    n_pairs = int((AD.toarray() > 0).sum() + ((DP - AD).toarray() > 0).sum())
+    lib = _lib.load()
+    for kind in (0, 1, 2):
+        for ori in (0, 1):
+            out = (ctypes.c_int64 * 4)()
+            _lib.check(lib.vb_seg_verify(counts.handle, kind, ori, out))
+            assert out[0] == n_pairs, (kind, ori, list(out), n_pairs)
+            assert out[1] == 0, "format kind %d pass %d: %d errors %s" % (kind, ori, out[1], list(out))

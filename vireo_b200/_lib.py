@@ -67,6 +67,7 @@ SIGNATURES = {
     "vb_counts_slice": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),
     "vb_counts_info": (C.c_int64, [C.c_void_p, C.c_int]),
     "vb_counts_note": (C.c_char_p, [C.c_void_p]),
+    "vb_seg_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "vb_binom_const": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "vb_vireo_ws_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(WsSizes)]),
     "vb_log_prior": (C.c_int, [c_dp, C.c_int64, C.c_int, c_dp, c_dp, C.c_void_p]),
@@ -98,6 +99,7 @@ SIGNATURES = {
     "vb_host_digamma": (C.c_double, [C.c_double]),
     "vb_host_beta_kl": (C.c_double, [C.c_double, C.c_double, C.c_double, C.c_double]),
     "vb_host_binom_term": (C.c_float, [C.c_uint32, C.c_uint32]),
+    "vb_host_seg_count_code": (C.c_uint32, [C.c_uint32, C.c_int]),
 }
 
 _lib = None

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", f) for f in ("vb_stage.cu", "vb_em.cu", "vb_seg.cu")]
 DEPS = SRC + [os.path.join(HERE, "csrc", "vb_common.cuh"), os.path.join(HERE, "csrc", "vb_stream.cuh"),
-              os.path.join(os.path.dirname(HERE), "include", "vireo_b200.h")]
+              os.path.join(HERE, "csrc", "vb_tail.cuh"), os.path.join(os.path.dirname(HERE), "include", "vireo_b200.h")]
 LIB = os.path.join(HERE, "libvireo_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -26,7 +26,11 @@ def nvcc_path():
 
 
 # sanitizer variants: same sources, one macro (see vb_seg.cu); built on demand, loaded through VIREO_B200_LIB
-VARIANTS = {"plainfill": ["-DVB_SEG_PLAIN_FILL", "-DVB_SEG_CANARY"], "canary": ["-DVB_SEG_CANARY"]}
+VARIANTS = {"plainfill": ["-DVB_SEG_PLAIN_FILL", "-DVB_SEG_CANARY"], "canary": ["-DVB_SEG_CANARY"],
+            # timing diagnostics of the segment kernels (results are garbage by design): no table loads / no window
+            # synchronisation in the consumer warps / both
+            "nolds": ["-DVB_SEG_DIAG_NOLDS"], "nosync": ["-DVB_SEG_DIAG_NOSYNC"],
+            "noldsnosync": ["-DVB_SEG_DIAG_NOLDS", "-DVB_SEG_DIAG_NOSYNC"]}
 
 
 def up_to_date(lib=LIB):
@@ -37,17 +41,37 @@ def up_to_date(lib=LIB):
 
 
 def build(force=False, verbose=False, variant=None):
+    """One object per source (compiled in parallel, re-used while the source and the headers are older), then the
+    link -- a full build is as long as its slowest file."""
     lib = LIB if variant is None else LIB.replace(".so", "_%s.so" % variant)
     if not force and up_to_date(lib):
         return lib
-    cmd = [nvcc_path(), "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", "-shared",
-           *(VARIANTS[variant] if variant else []),
-           "-Xptxas", "-v" if verbose else "-O3", "-o", lib, *SRC, "-ldl"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "_build", variant or "default")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [d for d in DEPS if d not in SRC]
+    flags = ["-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", *(VARIANTS[variant] if variant else []),
+             "-Xptxas", "-v" if verbose else "-O3"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if (not force and os.path.exists(obj)
+                and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in [src] + headers)):
+            return obj, 0, ""
+        res = subprocess.run([nvcc_path(), *flags, "-c", "-o", obj, src], capture_output=True, text=True)
+        return obj, res.returncode, res.stdout + res.stderr
+
+    with ThreadPoolExecutor(len(SRC)) as ex:
+        done = list(ex.map(compile_one, SRC))
+    for obj, rc, log in done:
+        if verbose or rc != 0:
+            sys.stderr.write(log)
+        if rc != 0:
+            raise RuntimeError("nvcc failed (exit %d) on %s:\n%s" % (rc, obj, log[-4000:]))
+    res = subprocess.run([nvcc_path(), *ARCH, "-shared", "-o", lib, *[o for o, _, _ in done], "-ldl"],
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed (exit %d):\n%s" % (res.returncode, res.stderr[-4000:]))
+        raise RuntimeError("link failed (exit %d):\n%s" % (res.returncode, res.stderr[-4000:]))
     return lib
 
 

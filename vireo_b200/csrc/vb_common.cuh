@@ -30,41 +30,45 @@
 
 // ----------------------------------------------------------------------------------------------
 // Window-segment format (vb_seg.cu), one per pass orientation and table precision.
-//   The gather table is cut into windows of
-//   `win_rows` rows; owners are sorted by pair count and packed VB_SEG_OWNERS = 32 to a warp task.
-//   For task t and window w the task's pairs with a gather row inside w form nsteps[t][w]
-//   "super-steps" of 32 records (one per owner slot, 64 bytes); owners with fewer pairs in the
-//   window are padded with null records.  Record (16 bits):
-//       bits 15..5  gather row - w * win_rows        bits 4..0  count (0 = null)
-//   Pairs with count > 31 and all pairs of very short owners go to a residual CSR.
+//   The gather table streams through a ring of `nb` window buffers of `win_rows` rows in shared memory: window w
+//   lives in buffer w % nb, so row r always sits at ring row r % (nb * win_rows) -- a record carries that ring row and
+//   the kernel needs no per-window base.  Owners are sorted by pair count and packed VB_SEG_OWNERS = 32 to a warp
+//   task.  A task's stream is a sequence of "super-steps" of 32 records (one per owner slot, 128 bytes).  While a warp
+//   is in *segment* s it holds the windows s .. s + span - 1; a segment carries every pair of window s that is still
+//   open and, in the slots lock-step would otherwise pad, pairs of the next span - 1 windows (earliest window first).
+//   Record (32 bits):
+//       bits 31..28  windows to advance BEFORE this super-step (only in the first slot of every lane group, 0 elsewhere)
+//       bits 27..16  ring row
+//       bits 15..0   FP64 tables: the upper 16 bits of the double 2 * count (sign, exponent, 4 mantissa bits: every
+//                    count with at most 5 significant bits is exact); fixed-point tables: the count (<= 31);  0 = null
+//   Pairs whose count has no such code and all pairs of very short owners go to a residual CSR.
 //   The kernel binds 4 lanes to one owner slot (4 columns per lane; 2 for the 8-column FP64 tables), so one warp
 //   step serves 8 owners and the 32 slots of a super-step take 4 steps.
 // ----------------------------------------------------------------------------------------------
 #define VB_SEG_OWNERS 32
 #define VB_SEG_MAX_WARPS 22               // consumer warps per CTA (+1 producer warp)
-#define VB_SEG_CNT_BITS 5
-#define VB_SEG_MAX_COUNT 31
-#define VB_SEG_MAX_WIN_ROWS 2048
-#define VB_SEG_DEPTH64 4                  // super-steps of records in flight per warp, FP64 tables (8 B per lane each)
-#define VB_SEG_L2_AHEAD 4096              // bytes of the record stream requested into L2 ahead of the register queue
-#define VB_SEG_DEPTH32 4                  // same, fixed-point tables (8 B per lane each)
+#define VB_SEG_DEPTH 4                    // a task's stream is padded to a multiple of this many super-steps
+#define VB_SEG_ADV_MAX 15                 // window advances one super-step can carry
+#define VB_SEG_MAX_RING_ROWS 4096         // 12-bit ring row
+#define VB_SEG_MAX_NB 16
+#define VB_SEG_L2_AHEAD 8192              // bytes of the record stream requested into L2 ahead of the register queue
 
 struct SegSet {
     int built;
     int64_t n_owner, n_gather;
     int64_t n_task;          // ceil(n_owner / 32) tasks in sorted order (longest owners first)
     int64_t n_task_stream;   // the first n_task_stream tasks carry records; the rest only need the epilogue
-    int n_win, win_rows, nb; // windows of the table, rows per window, windows resident in shared memory
-    int look;                // 1: a segment also carries pairs of the next window (look-ahead fill)
-    int depth;               // super-steps per group of the record queue (segments are padded to a multiple)
+    int n_win, win_rows, nb; // windows of the table, rows per window, window buffers in shared memory
+    int span;                // windows a warp holds at a time (1 + look-ahead windows)
+    int fixed;               // count code of the records: 0 upper half of the double 2 * count, 1 the integer
     int64_t n_step;          // super-steps in total
     int64_t n_light;         // pairs carried by the streams
     int64_t n_heavy;         // pairs in the residual
     int64_t max_reads;       // largest sum of counts over one owner's stream pairs (fixed-point error bound)
     int32_t* perm;           // [n_task*32] owner id of each slot, -1 = padding
-    uint16_t* nsteps;        // [n_task_stream * n_win]
-    int64_t* task_off;       // [n_task_stream + 1] first super-step of each task
-    uint16_t* rec;           // [n_step*32 + slack]
+    int64_t* task_off;       // [n_task_stream + 1] first super-step of each task (multiples of VB_SEG_DEPTH)
+    int32_t* tail;           // [n_task_stream] window advances left when a task's stream ends
+    uint32_t* rec;           // [n_step*32 + slack]
     int64_t* hptr;           // [n_owner+1] residual CSR
     int32_t* hrow;
     uint32_t* hcnt;
@@ -74,11 +78,11 @@ struct SegSet {
 
 struct SegView {
     int64_t n_owner, n_gather, n_task, n_task_stream;
-    int n_win, win_rows, look;
+    int n_win, win_rows, nb, span;
     const int32_t* __restrict__ perm;
-    const uint16_t* __restrict__ nsteps;
     const int64_t* __restrict__ task_off;
-    const uint16_t* __restrict__ rec;
+    const int32_t* __restrict__ tail;
+    const uint32_t* __restrict__ rec;
     const int64_t* __restrict__ hptr;
     const int32_t* __restrict__ hrow;
     const uint32_t* __restrict__ hcnt;

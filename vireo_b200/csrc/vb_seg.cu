@@ -8,21 +8,25 @@
 //   SNP  pass  S2[i,:] = sum_j (dp-ad)_ij * ID_prob[j,:],  S1[i,:] = sum_j ad_ij * ID_prob[j,:]
 //              (vireo_model.py:168-170,207-209, bmm_model.py:136-138)
 // What bounds such a pass on B200 is the shared-memory crossbar (128 B/clk/SM): every pair needs one
-// table row.  A lane-per-owner layout (the retired gather-stream kernels of round 1) spends 1.5 crossbar
-// wavefronts per 128-byte row because a quarter warp is rarely full.  Here
+// table row.  Here
 //   * 4 lanes share one owner and read its table row with 16-byte loads (two per lane for a 128-byte
 //     FP64 row -- one from each 64-byte half, even lane groups starting in the lower half and odd groups
 //     in the upper half so that the two rows of a wavefront never meet in a bank; one per lane for the
 //     64-byte rows), so a wavefront always carries whole rows;
 //   * a warp task holds 32 owners: 8 of them are served per warp step, the accumulators of all 32
 //     stay in registers (static indexing: the slot index is the unrolled loop variable);
-//   * the table streams through NB window buffers; a producer warp refills a buffer when every
-//     consumer warp has released it (full/empty mbarriers), consumers wait per window, not per record;
-//   * the records of a task are stored per window as super-steps of 32 x 16 bits; a segment (the
-//     super-steps of one window) may also carry pairs of the NEXT window, which is resident as well,
-//     in the slots that lock-step would otherwise pad with null records (look-ahead fill: 59% -> 85%
-//     useful slots); segments are padded to groups of DEPTH super-steps so that the register queue
-//     that prefetches them DEPTH super-steps ahead needs no rotation;
+//   * the table streams through a ring of NB window buffers; window w lives in buffer w % NB, so a table row
+//     has ONE shared-memory address for the whole pass and the records carry it (no per-window base, no wrap
+//     test).  A producer warp refills a buffer when every consumer warp has released it (full/empty mbarriers);
+//   * the records of a task are ONE stream of super-steps of 32 x 32 bits.  A warp holds `span` consecutive
+//     windows at a time; the planner (k_sg_plan) schedules every owner's pairs earliest-window-first into
+//     lock-step super-steps: a super-step is added only while some owner still has a pair in the oldest held
+//     window, every other owner uses the slot for its next pair inside the held windows (null record if it has
+//     none).  The windows to advance before a super-step are part of the record, so the kernel's loop has no
+//     per-window bookkeeping: decode, two loads, four FMAs per slot;
+//   * the count is stored as the upper 16 bits of the double 2 * count: one shift makes the FMA operand, and
+//     because those bits are the same for every count the address is ONE shift-add of the whole record (the
+//     stray bits are a constant folded into the lane base).  The factor 2 leaves in the epilogue (exact);
 //   * PREC 0: FP64 tables of 16 columns (rows of 128 bytes);  PREC 2: FP64 tables of 8 columns for
 //     n_donor <= 8 (rows of 64 bytes);  PREC 1 (opt-in) keeps 16 columns as unsigned 32-bit fixed point
 //     (rows of 64 bytes: half the crossbar traffic) and accumulates count * value exactly in 64-bit
@@ -33,6 +37,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <type_traits>
 #include <vector>
 
@@ -41,17 +46,48 @@
 #include "vb_tail.cuh"
 
 // ---------------------------------------------------------------------------------------------
+// count codes
+// ---------------------------------------------------------------------------------------------
+// FP64 tables: a count rides in a record when 2 * count is exact in a double cut to 4 mantissa bits, i.e. when it has
+// at most 5 significant bits (1..31, 32, 34, ..., 62, 64, 68, ...); fixed-point tables: counts up to 31.
+__host__ __device__ inline bool seg_count_ok(uint32_t c, int fixed) {
+    if (fixed) return c <= 31u;
+    if (c >= (1u << 24)) return false;
+    uint32_t t = c;
+    while (t >= 32u) { if (t & 1u) return false; t >>= 1; }
+    return true;
+}
+__host__ __device__ inline uint32_t seg_count_code(uint32_t c, int fixed) {
+    if (fixed) return c;
+    // 2c = m * 2^e with 16 <= m < 32 (or c < 16: subnormal-free small integers): build the upper half directly
+    uint32_t v = 2u * c, e = 0;
+    while ((v >> (e + 1)) != 0) ++e;                    // floor(log2(v))
+    const uint32_t mant4 = e >= 4 ? (v >> (e - 4)) & 0xfu : (v << (4 - e)) & 0xfu;
+    return ((1023u + e) << 4) | mant4;
+}
+__host__ __device__ inline uint32_t seg_code_count(uint32_t code, int fixed) {
+    if (fixed) return code;
+    const uint32_t e = (code >> 4) - 1023u, m = 16u | (code & 0xfu);      // value = m * 2^(e-4) = 2 * count
+    return (e >= 4 ? m << (e - 4) : m >> (4 - e)) >> 1;
+}
+
+// host-callable copy for the CPU test-suite: the code of `count`, or 0xffffffff when the count has no code
+extern "C" uint32_t vb_host_seg_count_code(uint32_t count, int fixed) {
+    return count != 0 && seg_count_ok(count, fixed) ? seg_count_code(count, fixed) : 0xffffffffu;
+}
+
+// ---------------------------------------------------------------------------------------------
 // build kernels
 // ---------------------------------------------------------------------------------------------
 
-// pairs per owner: stream pairs (count <= 31), residual pairs, reads carried by the stream pairs
+// pairs per owner: stream pairs (count has a code), residual pairs, reads carried by the stream pairs
 template <int ORI, bool WIDE>
-__global__ void k_sg_count(const CountsView m, int64_t n_owner, uint32_t* __restrict__ n_light, uint32_t* __restrict__ n_heavy,
+__global__ void k_sg_count(const CountsView m, int64_t n_owner, int fixed, uint32_t* __restrict__ n_light, uint32_t* __restrict__ n_heavy,
                            uint32_t* __restrict__ reads, unsigned int* flags) {
     for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n_owner; o += (int64_t)gridDim.x * blockDim.x) {
         uint32_t nl = 0, nh = 0, rd = 0;
         const bool ok = for_records<ORI, WIDE>(m, o, [&](int, uint32_t c) {
-            if (c > VB_SEG_MAX_COUNT) ++nh;
+            if (!seg_count_ok(c, fixed)) ++nh;
             else { ++nl; rd += c; }
         });
         if (!ok) atomicOr(&flags[0], 1u);
@@ -98,14 +134,14 @@ __global__ void k_sg_sums(const uint32_t* __restrict__ a, const uint32_t* __rest
 // pairs of each stream owner per table window; one thread per sorted position
 template <int ORI, bool WIDE>
 __global__ void k_sg_wincount(const CountsView m, int64_t n_active, const int32_t* __restrict__ perm, int win_rows, int n_win,
-                              uint16_t* __restrict__ cnt) {
+                              int fixed, uint16_t* __restrict__ cnt) {
     for (int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pos < n_active; pos += (int64_t)gridDim.x * blockDim.x) {
         const int64_t o = perm[pos];
         uint16_t* row = cnt + (size_t)pos * n_win;
         int w = 0;
         uint32_t n = 0;
         for_records<ORI, WIDE>(m, o, [&](int g, uint32_t c) {
-            if (c > VB_SEG_MAX_COUNT) return;
+            if (!seg_count_ok(c, fixed)) return;
             const int gw = g / win_rows;
             if (gw != w) { if (n) row[w] = (uint16_t)n; w = gw; n = 0; }
             ++n;
@@ -114,38 +150,52 @@ __global__ void k_sg_wincount(const CountsView m, int64_t n_active, const int32_
     }
 }
 
-// Segment plan, one thread per streaming task.  Segment w holds, for every owner slot, the owner's pairs of
-// window w that segment w-1 did not take, followed by up to `slack` pairs of window w+1 (look-ahead fill), where
-// slack = segment length - own pairs and the segment length is the largest own-pair count of the 32 owners.
-//   nsteps[t][w] super-steps of the segment, take[pos][w] pairs of window w+1 that owner `pos` serves in segment w,
-//   wide[t][w]   nsteps rounded up to a multiple of `depth` (stream positions)
-__global__ void k_sg_plan(const uint16_t* __restrict__ cnt, int64_t n_active, int64_t n_task_stream, int n_win, int look,
-                          int depth, uint16_t* __restrict__ nsteps, uint16_t* __restrict__ take, int64_t* __restrict__ wide) {
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t <= n_task_stream; t += (int64_t)gridDim.x * blockDim.x) {
-        if (t == n_task_stream) { wide[t * n_win] = 0; continue; }
-        uint16_t carry[VB_SEG_OWNERS];
-        for (int sl = 0; sl < VB_SEG_OWNERS; ++sl) carry[sl] = 0;
-        for (int w = 0; w < n_win; ++w) {
-            int n = 0;
-            for (int sl = 0; sl < VB_SEG_OWNERS; ++sl) {
-                const int64_t pos = t * VB_SEG_OWNERS + sl;
-                if (pos < n_active) { const int own = (int)cnt[(size_t)pos * n_win + w] - (int)carry[sl]; n = own > n ? own : n; }
-            }
-            for (int sl = 0; sl < VB_SEG_OWNERS; ++sl) {
-                const int64_t pos = t * VB_SEG_OWNERS + sl;
-                if (pos >= n_active) continue;
-                const int own = (int)cnt[(size_t)pos * n_win + w] - (int)carry[sl];
-                int tk = 0;
-                if (look && w + 1 < n_win) {
-                    const int nxt = cnt[(size_t)pos * n_win + w + 1];
-                    tk = n - own < nxt ? n - own : nxt;
-                }
-                take[(size_t)pos * n_win + w] = (uint16_t)tk;
-                carry[sl] = (uint16_t)tk;
-            }
-            nsteps[t * n_win + w] = (uint16_t)n;
-            wide[t * n_win + w] = (int64_t)((n + depth - 1) / depth) * depth;
+// The lock-step schedule of one task, one warp per task, lane = owner slot.  In segment s the warp holds the windows
+// s .. s + span - 1.  Every owner runs its pairs earliest window first; the segment lasts as long as some owner still
+// has a pair of window s (which leaves the ring next), and in every one of its super-steps each owner with a pair
+// inside the held windows executes one.  That is the shortest lock-step schedule for the given span.
+//   cnt[pos][s]   in: pairs of the owner in window s;  out: pairs the owner executes during segment s
+//   segn[t][s]    super-steps of segment s            adv[t][s]  windows to advance before its first super-step
+//   wide[t][s]    = segn, the last one of a task padded so that the task's total is a multiple of `depth`
+//   tail[t]       window advances left when the stream ends (the warp releases every window of the table)
+// An empty segment passes its advance on to the next super-step; a run of VB_SEG_ADV_MAX empty segments gets a null
+// super-step to carry the advances.
+__global__ void __launch_bounds__(256)
+k_sg_plan(uint16_t* __restrict__ cnt, int64_t n_active, int64_t n_task_stream, int n_win, int span, int depth,
+          uint16_t* __restrict__ segn, uint8_t* __restrict__ adv, int64_t* __restrict__ wide, int32_t* __restrict__ tail) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (t > n_task_stream) return;
+    if (t == n_task_stream) { if (lane == 0) wide[t * n_win] = 0; return; }
+    const int64_t pos = t * VB_SEG_OWNERS + lane;
+    const bool active = pos < n_active;
+    uint16_t* row = cnt + (size_t)(active ? pos : 0) * n_win;
+    uint32_t consumed = 0, cum_own = 0, cum_held = 0, pending = 0;
+    int64_t total = 0;
+    for (int w = 0; w < span - 1 && w < n_win; ++w) cum_held += active ? row[w] : 0u;
+    for (int s = 0; s < n_win; ++s) {
+        cum_own += active ? row[s] : 0u;
+        if (s + span - 1 < n_win) cum_held += active ? row[s + span - 1] : 0u;
+        uint32_t n = cum_own > consumed ? cum_own - consumed : 0u;      // pairs that must run before window s is released
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { const uint32_t o = __shfl_xor_sync(VB_FULL, n, off); n = o > n ? o : n; }
+        if (s > 0) ++pending;
+        if (n == 0 && pending >= VB_SEG_ADV_MAX) n = 1;
+        const uint32_t avail = cum_held - consumed;
+        const uint32_t e = n < avail ? n : avail;
+        consumed += e;
+        if (active) row[s] = (uint16_t)e;
+        if (lane == 0) {
+            segn[t * n_win + s] = (uint16_t)n;
+            adv[t * n_win + s] = (uint8_t)(n ? pending : 0u);
+            wide[t * n_win + s] = (int64_t)n;
         }
+        if (n) pending = 0;
+        total += n;
+    }
+    if (lane == 0) {
+        wide[t * n_win + n_win - 1] += (total + depth - 1) / depth * depth - total;
+        tail[t] = (int32_t)pending + 1;      // advances the stream does not carry: the warp releases all n_win windows
     }
 }
 
@@ -154,16 +204,26 @@ __global__ void k_sg_widen(const uint32_t* __restrict__ in, int64_t n, int64_t* 
         out[i] = i < n ? (int64_t)in[i] : 0;
 }
 
-// write the records and the residual CSR; one thread per sorted position.  Within window v the owner's first
-// take[v-1] pairs belong to segment v-1 (row offsets relative to window v-1, i.e. >= win_rows), the rest to segment v.
-// The order of an owner's records inside a segment is free.  With 64-byte table rows (`pair_dist` > 0) two owner
-// slots share one shared-memory wavefront (slots s and s + pair_dist of a super-step): rows of equal parity hit the
-// same 16 banks.  Slot s therefore lists its even rows from the front and its odd rows from the back of the segment,
-// slot s + pair_dist the other way round, so that most steps pair an even with an odd row.
+// the windows to advance before the first super-step of every non-empty segment, in the first slot of each lane group
+__global__ void k_sg_mark_adv(const uint16_t* __restrict__ segn, const uint8_t* __restrict__ adv, const int64_t* __restrict__ step_off,
+                              int64_t n_tw, uint32_t* __restrict__ rec) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_tw; i += (int64_t)gridDim.x * blockDim.x) {
+        if (segn[i] == 0 || adv[i] == 0) continue;
+        uint32_t* ss = rec + (size_t)step_off[i] * VB_SEG_OWNERS;
+        for (int j = 0; j < VB_SEG_OWNERS; j += 4) ss[j] = (uint32_t)adv[i] << 28;
+    }
+}
+
+// write the records and the residual CSR; one thread per sorted position.  The owner's pairs, in gather-row order,
+// fill its slot of segment 0's first exec[pos][0] super-steps, then segment 1's, ...  The order of an owner's records
+// inside a segment is free.  With 64-byte table rows (`pair_dist` > 0) two owner slots share one shared-memory
+// wavefront (slots s and s + pair_dist of a super-step): rows of equal parity hit the same 16 banks.  Slot s
+// therefore lists its even rows from the front and its odd rows from the back of the segment, slot s + pair_dist the
+// other way round, so that most steps pair an even with an odd row.
 template <int ORI, bool WIDE>
-__global__ void k_sg_fill(const CountsView m, int64_t n_owner, int64_t n_active, const int32_t* __restrict__ perm, int win_rows,
-                          int n_win, int pair_dist, const int64_t* __restrict__ step_off, const uint16_t* __restrict__ cnt,
-                          const uint16_t* __restrict__ take, uint16_t* __restrict__ rec,
+__global__ void k_sg_fill(const CountsView m, int64_t n_owner, int64_t n_active, const int32_t* __restrict__ perm, int ring_rows,
+                          int n_win, int fixed, int pair_dist, const int64_t* __restrict__ step_off,
+                          const uint16_t* __restrict__ exec, uint32_t* __restrict__ rec,
                           const int64_t* __restrict__ hptr, int32_t* __restrict__ hrow, uint32_t* __restrict__ hcnt) {
     for (int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pos < n_owner; pos += (int64_t)gridDim.x * blockDim.x) {
         const int64_t o = perm[pos];
@@ -171,41 +231,27 @@ __global__ void k_sg_fill(const CountsView m, int64_t n_owner, int64_t n_active,
         const int64_t t = pos / VB_SEG_OWNERS;
         const int slot = (int)(pos % VB_SEG_OWNERS);
         const uint32_t front_parity = (pair_dist > 0 && (slot & pair_dist)) ? 1u : 0u;    // row parity listed from the front
-        const uint16_t* crow = cnt + (size_t)pos * n_win;
-        const uint16_t* trow = take + (size_t)pos * n_win;
+        const uint16_t* erow = exec + (size_t)(streams ? pos : 0) * n_win;
         int64_t h = hptr[o];
-        int w = -1;
-        int k = 0;                 // index of the pair inside its window
-        int early = 0;             // pairs of window w served by segment w-1
-        // per segment: first super-step, records of this owner, cursors from the front and from the back
-        int64_t base_prev = 0, base_cur = 0;
-        int tot_prev = 0, tot_cur = 0, f_prev = 0, b_prev = 0, f_cur = 0, b_cur = 0;
+        int seg = -1;
+        int k = 0, e_cur = 0, f = 0, b = 0;       // pairs placed in the segment, its pairs, cursors from the front / the back
+        int64_t base = 0;
         for_records<ORI, WIDE>(m, o, [&](int g, uint32_t c) {
-            if (c > VB_SEG_MAX_COUNT || !streams) { hrow[h] = g; hcnt[h] = c; ++h; return; }
-            const int gw = g / win_rows;
-            if (gw != w) {
-                if (gw == w + 1 && w >= 0) { base_prev = base_cur; tot_prev = tot_cur; f_prev = f_cur; b_prev = b_cur; }
-                else if (gw > 0) {      // the segment before gw holds only early pairs of this window (none of its own)
-                    base_prev = step_off[t * n_win + gw - 1];
-                    tot_prev = (int)crow[gw - 1] - (gw > 1 ? (int)trow[gw - 2] : 0) + (int)trow[gw - 1];
-                    f_prev = b_prev = 0;
-                }
-                w = gw; k = 0;
-                early = w > 0 ? trow[w - 1] : 0;
-                base_cur = step_off[t * n_win + w];
-                tot_cur = (int)crow[w] - early + (int)trow[w];
-                f_cur = b_cur = 0;
+            if (!streams || !seg_count_ok(c, fixed)) { hrow[h] = g; hcnt[h] = c; ++h; return; }
+            while (k == e_cur) {
+                if (seg + 1 >= n_win) return;       // cannot happen: the plan executes every pair by its own window
+                ++seg;
+                k = f = b = 0;
+                e_cur = erow[seg];
+                base = step_off[t * n_win + seg];
             }
-            int64_t s;
-            uint32_t rel;
-            if (k < early) {
-                rel = (uint32_t)(g - (gw - 1) * win_rows);
-                s = pair_dist == 0 ? base_prev + f_prev++ : ((rel & 1u) == front_parity ? base_prev + f_prev++ : base_prev + tot_prev - 1 - b_prev++);
-            } else {
-                rel = (uint32_t)(g - gw * win_rows);
-                s = pair_dist == 0 ? base_cur + f_cur++ : ((rel & 1u) == front_parity ? base_cur + f_cur++ : base_cur + tot_cur - 1 - b_cur++);
-            }
-            rec[(size_t)s * VB_SEG_OWNERS + slot] = (uint16_t)((rel << VB_SEG_CNT_BITS) | c);
+            const uint32_t rr = (uint32_t)(g % ring_rows);
+            int at;
+            if (pair_dist == 0 || (rr & 1u) == front_parity) at = f++;
+            else at = e_cur - 1 - b++;
+            uint32_t* dst = rec + ((size_t)(base + at) * VB_SEG_OWNERS + slot);
+            const uint32_t keep = (slot & 3) == 0 ? (*dst & 0xf0000000u) : 0u;        // k_sg_mark_adv ran before
+            *dst = keep | (rr << 16) | seg_count_code(c, fixed);
             ++k;
         });
     }
@@ -215,7 +261,7 @@ __global__ void k_sg_fill(const CountsView m, int64_t n_owner, int64_t n_active,
 // host: build one orientation
 // ---------------------------------------------------------------------------------------------
 static void seg_set_free(SegSet& g) {
-    cudaFree(g.perm); cudaFree(g.nsteps); cudaFree(g.task_off); cudaFree(g.rec);
+    cudaFree(g.perm); cudaFree(g.task_off); cudaFree(g.tail); cudaFree(g.rec);
     cudaFree(g.hptr); cudaFree(g.hrow); cudaFree(g.hcnt);
     memset(&g, 0, sizeof(g));
 }
@@ -233,25 +279,23 @@ static int env_int(const char* name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 
-// window geometry per table precision: rows per window and resident windows (shared memory: nb * rows * row bytes).
-// Look-ahead fill needs the windows w and w+1 resident while w+2 loads: nb >= 3.
-static void seg_window(int prec, int* win_rows, int* nb, int* look) {
-    if (prec == 0) { *win_rows = env_int("VIREO_B200_SEG_WR64", 512); *nb = env_int("VIREO_B200_SEG_NB64", 3); }
-    else { *win_rows = env_int("VIREO_B200_SEG_WR32", 1024); *nb = env_int("VIREO_B200_SEG_NB32", 3); }     // 64-byte rows
-    *look = env_int("VIREO_B200_SEG_LOOK", 1) ? 1 : 0;
-    if (*win_rows < 32) *win_rows = 32;
-    if (*win_rows > VB_SEG_MAX_WIN_ROWS / 2) *win_rows = VB_SEG_MAX_WIN_ROWS / 2;     // 11-bit row offsets span two windows
-    *win_rows &= ~7;
-    if (*nb < 2) *nb = 2;
+// ring geometry per table precision: rows per window, window buffers (shared memory: nb * rows * row bytes) and the
+// windows a warp holds at a time.  nb - span buffers are what the producer can refill while the slowest warp still
+// holds its oldest window.
+static void seg_window(int prec, int* win_rows, int* nb, int* span) {
+    if (prec == 0) {
+        *win_rows = env_int("VIREO_B200_SEG_WR64", 256); *nb = env_int("VIREO_B200_SEG_NB64", 6); *span = env_int("VIREO_B200_SEG_SPAN64", 4);
+    } else {                                                                                     // 64-byte rows
+        *win_rows = env_int("VIREO_B200_SEG_WR32", 512); *nb = env_int("VIREO_B200_SEG_NB32", 6); *span = env_int("VIREO_B200_SEG_SPAN32", 4);
+    }
     const int row_bytes = prec == 0 ? 128 : 64;
-    while ((size_t)*nb * *win_rows * row_bytes > 200 * 1024 && *nb > 3) --*nb;
-    while ((size_t)*nb * *win_rows * row_bytes > 200 * 1024) *win_rows -= 8;
-    if (*nb < 3) *look = 0;
-}
-
-static int seg_depth(int prec) {
-    const int d = env_int(prec == 0 ? "VIREO_B200_SEG_DEPTH64" : "VIREO_B200_SEG_DEPTH32", prec == 0 ? VB_SEG_DEPTH64 : VB_SEG_DEPTH32);
-    return (d >= 8 && prec != 2) ? 8 : 4;
+    if (*nb < 2) *nb = 2;
+    if (*nb > VB_SEG_MAX_NB) *nb = VB_SEG_MAX_NB;
+    if (*win_rows < 32) *win_rows = 32;
+    *win_rows &= ~7;
+    while ((size_t)*nb * *win_rows * row_bytes > 192 * 1024 || *nb * *win_rows > VB_SEG_MAX_RING_ROWS) *win_rows -= 8;
+    if (*span > *nb - 1) *span = *nb - 1;
+    if (*span < 1) *span = 1;
 }
 
 template <int ORI>
@@ -261,9 +305,10 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
     const int64_t O = ORI == 0 ? m->C : 2 * m->V;
     const int64_t Gn = ORI == 0 ? 2 * m->V : m->C;
     if (O >= (1ll << 31) - 64 || Gn >= (1ll << 31) - 4096) { vb_set_error("segment format: more than 2^31 rows"); return VB_E_UNSUPPORTED; }
-    int win_rows, nb, look;
-    seg_window(prec, &win_rows, &nb, &look);
-    const int depth = seg_depth(prec);
+    int win_rows, nb, span;
+    seg_window(prec, &win_rows, &nb, &span);
+    const int fixed = prec == 1 ? 1 : 0;
+    const int depth = VB_SEG_DEPTH;
     int n_win = (int)((Gn + win_rows - 1) / win_rows);
     if (n_win < 1) n_win = 1;
     const int64_t n_task = (O + VB_SEG_OWNERS - 1) / VB_SEG_OWNERS;
@@ -287,8 +332,8 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
     std::vector<uint32_t> hlen((size_t)O, 0u);
     int64_t n_active = 0;
     if (O) {
-        if (m->wide) k_sg_count<ORI, true><<<grid1d(O, sm), 256, 0, st>>>(v, O, nl, nh, rd, flags);
-        else k_sg_count<ORI, false><<<grid1d(O, sm), 256, 0, st>>>(v, O, nl, nh, rd, flags);
+        if (m->wide) k_sg_count<ORI, true><<<grid1d(O, sm), 256, 0, st>>>(v, O, fixed, nl, nh, rd, flags);
+        else k_sg_count<ORI, false><<<grid1d(O, sm), 256, 0, st>>>(v, O, fixed, nl, nh, rd, flags);
         VB_CUDA(cudaGetLastError());
         k_sg_iota<<<grid1d(O, sm), 256, 0, st>>>(ids, O);
         VB_CUDA(cudaGetLastError());
@@ -324,7 +369,7 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
         VB_CUDA(cudaMemcpyAsync(hsums, sums, sizeof(hsums), cudaMemcpyDeviceToHost, st));
         VB_CUDA(cudaStreamSynchronize(st));
     }
-    g.n_owner = O; g.n_gather = Gn; g.n_task = n_task; g.n_win = n_win; g.win_rows = win_rows; g.nb = nb; g.look = look; g.depth = depth;
+    g.n_owner = O; g.n_gather = Gn; g.n_task = n_task; g.n_win = n_win; g.win_rows = win_rows; g.nb = nb; g.span = span; g.fixed = fixed;
     g.n_light = (int64_t)hsums[0]; g.n_heavy = (int64_t)hsums[1]; g.max_reads = (int64_t)hsums[2];
     g.n_task_stream = (n_active + VB_SEG_OWNERS - 1) / VB_SEG_OWNERS;
     const int64_t nts = g.n_task_stream;
@@ -333,24 +378,24 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
     VB_CUDA(cudaMemsetAsync(g.perm, 0xff, (n_task ? n_task : 1) * VB_SEG_OWNERS * sizeof(int32_t), st));
     if (O) VB_CUDA(cudaMemcpyAsync(g.perm, perm_sorted, O * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
 
-    // super-steps per (task, window) and their offsets
+    // the schedule: super-steps per (task, segment) and their offsets
     const int64_t n_tw = nts * n_win;
-    uint16_t *cnt_ow, *take;
+    uint16_t *cnt_ow, *segn;
+    uint8_t* adv;
     int64_t *wide, *step_off;
     const size_t n_cw = (size_t)(n_active ? n_active : 1) * n_win;
-    if ((rc = tmp.alloc(&cnt_ow, n_cw)) || (rc = tmp.alloc(&take, n_cw)) || (rc = tmp.alloc(&wide, n_tw + 1)) ||
-        (rc = tmp.alloc(&step_off, n_tw + 1)))
+    if ((rc = tmp.alloc(&cnt_ow, n_cw)) || (rc = tmp.alloc(&segn, n_tw + 1)) || (rc = tmp.alloc(&adv, n_tw + 1)) ||
+        (rc = tmp.alloc(&wide, n_tw + 1)) || (rc = tmp.alloc(&step_off, n_tw + 1)))
         return rc;
-    VB_CUDA(cudaMalloc(&g.nsteps, (n_tw ? n_tw : 1) * sizeof(uint16_t)));
     VB_CUDA(cudaMalloc(&g.task_off, (nts + 1) * sizeof(int64_t)));
+    VB_CUDA(cudaMalloc(&g.tail, (nts + 1) * sizeof(int32_t)));
     VB_CUDA(cudaMemsetAsync(cnt_ow, 0, n_cw * sizeof(uint16_t), st));
-    VB_CUDA(cudaMemsetAsync(take, 0, n_cw * sizeof(uint16_t), st));
     if (n_active) {
-        if (m->wide) k_sg_wincount<ORI, true><<<grid1d(n_active, sm), 256, 0, st>>>(v, n_active, g.perm, win_rows, n_win, cnt_ow);
-        else k_sg_wincount<ORI, false><<<grid1d(n_active, sm), 256, 0, st>>>(v, n_active, g.perm, win_rows, n_win, cnt_ow);
+        if (m->wide) k_sg_wincount<ORI, true><<<grid1d(n_active, sm), 256, 0, st>>>(v, n_active, g.perm, win_rows, n_win, fixed, cnt_ow);
+        else k_sg_wincount<ORI, false><<<grid1d(n_active, sm), 256, 0, st>>>(v, n_active, g.perm, win_rows, n_win, fixed, cnt_ow);
         VB_CUDA(cudaGetLastError());
     }
-    k_sg_plan<<<grid1d(nts + 1, sm), 64, 0, st>>>(cnt_ow, n_active, nts, n_win, look, depth, g.nsteps, take, wide);
+    k_sg_plan<<<(unsigned)((nts + 1 + 7) / 8), 256, 0, st>>>(cnt_ow, n_active, nts, n_win, span, depth, segn, adv, wide, g.tail);
     VB_CUDA(cudaGetLastError());
     {
         size_t tb = 0;
@@ -382,12 +427,17 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
         VB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, hw, g.hptr, O + 1, st));
     }
     // slack: the register queue runs `depth` super-steps ahead, the L2 prefetch VB_SEG_L2_AHEAD bytes
-    const size_t n_rec = ((size_t)total_steps + 2 * depth) * VB_SEG_OWNERS + VB_SEG_L2_AHEAD / 2 + 64;
-    VB_CUDA(cudaMalloc(&g.rec, n_rec * sizeof(uint16_t)));
-    VB_CUDA(cudaMemsetAsync(g.rec, 0, n_rec * sizeof(uint16_t), st));
+    const size_t n_rec = ((size_t)total_steps + 2 * depth) * VB_SEG_OWNERS + VB_SEG_L2_AHEAD / 4 + 256;
+    VB_CUDA(cudaMalloc(&g.rec, n_rec * sizeof(uint32_t)));
+    VB_CUDA(cudaMemsetAsync(g.rec, 0, n_rec * sizeof(uint32_t), st));
+    if (n_tw) {
+        k_sg_mark_adv<<<grid1d(n_tw, sm), 256, 0, st>>>(segn, adv, step_off, n_tw, g.rec);
+        VB_CUDA(cudaGetLastError());
+    }
     if (O) {
-        if (m->wide) k_sg_fill<ORI, true><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, win_rows, n_win, prec != 0 ? 4 : 0, step_off, cnt_ow, take, g.rec, g.hptr, g.hrow, g.hcnt);
-        else k_sg_fill<ORI, false><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, win_rows, n_win, prec != 0 ? 4 : 0, step_off, cnt_ow, take, g.rec, g.hptr, g.hrow, g.hcnt);
+        const int pair_dist = prec != 0 ? 4 : 0;
+        if (m->wide) k_sg_fill<ORI, true><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, nb * win_rows, n_win, fixed, pair_dist, step_off, cnt_ow, g.rec, g.hptr, g.hrow, g.hcnt);
+        else k_sg_fill<ORI, false><<<grid1d(O, sm), 256, 0, st>>>(v, O, n_active, g.perm, nb * win_rows, n_win, fixed, pair_dist, step_off, cnt_ow, g.rec, g.hptr, g.hrow, g.hcnt);
         VB_CUDA(cudaGetLastError());
     }
     VB_CUDA(cudaStreamSynchronize(st));
@@ -400,7 +450,7 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
     if (grid < 1) grid = 1;
     if (grid > 65535 * 16) { vb_set_error("segment format: too many owner rows"); return VB_E_UNSUPPORTED; }
     g.grid = (int)grid; g.nwarps = nw;
-    g.bytes = (int64_t)n_rec * 2 + n_task * VB_SEG_OWNERS * 4 + n_tw * 2 + (nts + 1) * 8 + (O + 1) * 8 + g.n_heavy * 8;
+    g.bytes = (int64_t)n_rec * 4 + n_task * VB_SEG_OWNERS * 4 + (nts + 1) * 8 + (O + 1) * 8 + g.n_heavy * 8;
     g.built = 1;
     return VB_OK;
 }
@@ -428,6 +478,85 @@ void vb_seg_free(vb_counts* m) {
 void vb_seg_geometry(const SegSet& g, int* grid, int* nwarps) {
     *grid = g.grid > 0 ? g.grid : 1;
     *nwarps = g.nwarps > 0 ? g.nwarps : 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// format check (tests): every pair of the staged counts appears exactly once -- as a record that executes while
+// its table row is inside the windows the warp holds, or in the residual CSR.  Host-side, for small matrices.
+//   out[0] pairs checked, out[1] errors, out[2] super-steps, out[3] null slots
+// ---------------------------------------------------------------------------------------------
+struct SegPair { int32_t owner, row; uint32_t count; };
+static bool operator<(const SegPair& a, const SegPair& b) {
+    if (a.owner != b.owner) return a.owner < b.owner;
+    if (a.row != b.row) return a.row < b.row;
+    return a.count < b.count;
+}
+static bool operator==(const SegPair& a, const SegPair& b) { return a.owner == b.owner && a.row == b.row && a.count == b.count; }
+
+template <typename T> static int seg_download(std::vector<T>& h, const T* d, size_t n) {
+    h.resize(n);
+    if (n) VB_CUDA(cudaMemcpy(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost));
+    return VB_OK;
+}
+
+extern "C" int vb_seg_verify(vb_counts* m, int prec, int ori, int64_t* out) {
+    if (!m || !out || prec < 0 || prec > 2) { vb_set_error("vb_seg_verify: bad arguments"); return VB_E_ARG; }
+    DeviceGuard dg(m->device);
+    int rc = vb_seg_build(m, prec, 0);
+    if (rc) return rc;
+    VB_CUDA(cudaDeviceSynchronize());
+    const SegSet& g = ori ? m->sB[prec] : m->sA[prec];
+    std::vector<int64_t> cptr, toff, hptr;
+    std::vector<int32_t> cidx, perm, hrow, tail;
+    std::vector<uint32_t> ccnt, cdp, rec, hcnt;
+    if ((rc = seg_download(cptr, m->cell_ptr, (size_t)m->C + 1)) || (rc = seg_download(cidx, m->cell_idx, (size_t)m->N)) ||
+        (rc = seg_download(ccnt, m->cell_cnt, (size_t)m->N)) || (m->wide && (rc = seg_download(cdp, m->cell_dp, (size_t)m->N))) ||
+        (rc = seg_download(toff, g.task_off, (size_t)g.n_task_stream + 1)) || (rc = seg_download(tail, g.tail, (size_t)g.n_task_stream)) || (rc = seg_download(perm, g.perm, (size_t)g.n_task * VB_SEG_OWNERS)) ||
+        (rc = seg_download(rec, g.rec, (size_t)g.n_step * VB_SEG_OWNERS)) || (rc = seg_download(hptr, g.hptr, (size_t)g.n_owner + 1)) ||
+        (rc = seg_download(hrow, g.hrow, (size_t)g.n_heavy)) || (rc = seg_download(hcnt, g.hcnt, (size_t)g.n_heavy)))
+        return rc;
+    std::vector<SegPair> truth, got;
+    for (int64_t j = 0; j < m->C; ++j)
+        for (int64_t q = cptr[j]; q < cptr[j + 1]; ++q) {
+            const uint32_t a = m->wide ? ccnt[q] : (ccnt[q] & 0xffffu), d = m->wide ? cdp[q] : (ccnt[q] >> 16);
+            const int32_t i = cidx[q];
+            if (d - a) truth.push_back(ori ? SegPair{2 * i, (int32_t)j, d - a} : SegPair{(int32_t)j, 2 * i, d - a});
+            if (a) truth.push_back(ori ? SegPair{2 * i + 1, (int32_t)j, a} : SegPair{(int32_t)j, 2 * i + 1, a});
+        }
+    int64_t errors = 0, nulls = 0;
+    const int64_t ring_rows = (int64_t)g.nb * g.win_rows;
+    for (int64_t t = 0; t < g.n_task_stream; ++t) {
+        if ((toff[t + 1] - toff[t]) % VB_SEG_DEPTH) ++errors;
+        int64_t s = 0;
+        for (int64_t u = toff[t]; u < toff[t + 1]; ++u) {
+            const uint32_t* ss = &rec[(size_t)u * VB_SEG_OWNERS];
+            const uint32_t adv = ss[0] >> 28;
+            s += adv;
+            if (s >= g.n_win) { ++errors; break; }
+            for (int sl = 0; sl < VB_SEG_OWNERS; ++sl) {
+                uint32_t w = ss[sl];
+                if ((w >> 28) != ((sl & 3) == 0 ? adv : 0u)) ++errors;
+                w &= 0x0fffffffu;
+                if ((w & 0xffffu) == 0) { ++nulls; if (w) ++errors; continue; }
+                const int64_t rr = w >> 16, lo = s * g.win_rows, hi = std::min<int64_t>((s + g.span) * (int64_t)g.win_rows, g.n_gather);
+                int64_t r = lo - lo % ring_rows + rr;
+                if (r < lo) r += ring_rows;
+                const int32_t owner = perm[(size_t)t * VB_SEG_OWNERS + sl];
+                if (r >= hi || owner < 0) { ++errors; continue; }
+                got.push_back(SegPair{owner, (int32_t)r, seg_code_count(w & 0xffffu, g.fixed)});
+            }
+        }
+        if (s + tail[t] != g.n_win) ++errors;            // stream + tail release every window exactly once
+    }
+    for (int64_t o = 0; o < g.n_owner; ++o)
+        for (int64_t q = hptr[o]; q < hptr[o + 1]; ++q) got.push_back(SegPair{(int32_t)o, hrow[q], hcnt[q]});
+    std::sort(truth.begin(), truth.end());
+    std::sort(got.begin(), got.end());
+    if (truth.size() != got.size()) errors += (int64_t)(truth.size() > got.size() ? truth.size() - got.size() : got.size() - truth.size());
+    for (size_t i = 0; i < truth.size() && i < got.size(); ++i)
+        if (!(truth[i] == got[i])) ++errors;
+    out[0] = (int64_t)truth.size(); out[1] = errors; out[2] = g.n_step; out[3] = nulls;
+    return VB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -494,15 +623,16 @@ __global__ void __launch_bounds__(VB_THREADS) k_seg_quant_rows(const double* __r
 // k_seg
 // ---------------------------------------------------------------------------------------------
 #define VB_SG_RED_DOUBLES (2 * VB_MAX_GT)
+#define VB_SG_RECBAR_OFF 256u        // record-chunk barriers of the consumer warps (two each) behind the window barriers
+#define VB_SG_RED_OFF 1024u         // block-reduction scratch
 #define VB_SG_PIECE 16384u          // bytes per bulk copy
+#define VB_SG_RING_OFF 4096u        // the window ring starts here in dynamic shared memory (barriers and scratch below)
 
 struct SegArgs {
     int mode;            // GM_CELL, GM_CELL_LL, GM_SNP
     int theta_mode;      // GM_SNP: 0 never, 1 always, 2 per the device iteration counter
     int nwarps;          // consumer warps per CTA (block size = (nwarps + 1) * 32)
-    int nb;              // resident windows
     int has_heavy;       // add p.H[owner] before the epilogue
-    int wait_hint_ns;    // > 0: suspend-time hint of the window waits
     int64_t table_stride;    // bytes per restart of the gather table
     const unsigned char* table;
     // GM_PLAIN: the sums of columns [0, plain_cols) go to plain_out[owner * plain_ld + plain_off + column]
@@ -512,84 +642,70 @@ struct SegArgs {
 };
 
 template <int PREC> struct SegCfg;
-template <> struct SegCfg<0> { static constexpr int LPO = 4, NC = 4, ROWB = 128; };
-template <> struct SegCfg<1> { static constexpr int LPO = 4, NC = 4, ROWB = 64; };
-template <> struct SegCfg<2> { static constexpr int LPO = 4, NC = 2, ROWB = 64; };     // FP64, 8 columns
+template <> struct SegCfg<0> { static constexpr int LPO = 4, NC = 4, ROWB = 128, SHIFT = 9; };
+template <> struct SegCfg<1> { static constexpr int LPO = 4, NC = 4, ROWB = 64, SHIFT = 10; };
+template <> struct SegCfg<2> { static constexpr int LPO = 4, NC = 2, ROWB = 64, SHIFT = 10; };     // FP64, 8 columns
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// One owner slot of one super-step.  `w` holds two 16-bit records; HI selects the upper one.  The row offset
-// (bits 15..5 of the record) times the row size gives the byte offset from the start of window w's buffer; a
-// record of the look-ahead window lands in the next buffer, which is contiguous unless the ring wraps (WRAP).
-// FP64 tables: 4 lanes x 4 columns, two 16-byte loads per lane.
+// One owner slot of one super-step.  Record w = ring row << 16 | count code (the advance bits are already cleared).
+// The shared-memory address of this lane's granule is ONE shift-add: w >> SHIFT = ring row * row bytes + the upper
+// bits of the count code, which are the same for every count (FP64: sign 0 and the exponent bits of 2 <= 2c < 2^26)
+// or zero (fixed point: count <= 31) -- `base` has that constant subtracted.  A null record (w = 0) computes an
+// address below its row 0 and loads nothing.
+// FP64 tables: 4 lanes x 4 columns, two 16-byte loads per lane, one from each 64-byte half of the row (even lane
+// groups start in the lower half, odd groups in the upper half: the two rows that share a wavefront never meet in a
+// bank).  The count operand is the record shifted into the upper word of a double: 2 * count, the epilogue halves.
+#ifdef VB_SEG_DIAG_NOLDS      // timing diagnostic (build.py variant "nolds"): the table loads never execute
+#define VB_SEG_SETP4 "setp.eq.u32 p, %4, 0xffffffff;\n\t"
+#define VB_SEG_SETP2 "setp.eq.u32 p, %2, 0xffffffff;\n\t"
+#else
+#define VB_SEG_SETP4 "setp.ne.u32 p, %4, 0;\n\t"
+#define VB_SEG_SETP2 "setp.ne.u32 p, %2, 0;\n\t"
+#endif
 struct SegScratch64 { double v[2][4]; };     // landing registers of the FP64 loads, two sets in flight
 struct SegScratch32 {};
-struct SegScratchN { double v[2][2]; };         // narrow FP64 rows: one 16-byte load per lane and record
+struct SegScratchN { double v[2][2]; };      // narrow FP64 rows: one 16-byte load per lane and record
 
-template <bool HI, bool WRAP>
-__device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes, double (&a)[4],
-                                         double (&v)[4]) {
-    const uint32_t c = HI ? (w & 0x001f0000u) : (w & 0x1fu);
-    uint32_t t;
-    asm("and.b32 %0, %1, %2;" : "=r"(t) : "r"(w), "r"(HI ? 0xffe00000u : 0xffe0u));   // opaque: keeps the scaling one LEA
-    uint32_t off = HI ? __umulhi(t, 1u << 18) : t * 4u;    // row offset * 128 bytes
-    if (WRAP && off >= wrap_at) off -= ring_bytes;
-    const uint32_t addr = base + off;
-    // `base` points at this lane's 16-byte granule in one half of the row; the other half is 64 bytes away (even
-    // lane groups start in the lower half, odd groups in the upper half: the two rows that share a wavefront never
-    // meet in a bank).
-    // count -> double without the conversion pipe: 2^52 + x is exact, subtracting 2^52 leaves x.  The upper record of
-    // a word is used in place (count << 16): odd slots carry a factor 2^16 that the epilogue removes.
-    const double d = __hiloint2double(0x43300000, (int)c) - 4503599627370496.0;
-    // Predicated loads, unconditional FMAs: a null record (count 0) issues no shared-memory wavefront, keeps
-    // whatever finite table values its landing registers held, and adds 0 * value.  (An `if` around loads and
-    // FMAs is compiled to a branch, which serialises consecutive slots on the load latency.)
+__device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, double (&a)[4], double (&v)[4]) {
+    const uint32_t xh = w << 16;
+    const uint32_t addr = (w >> 9) + base;
+    const double d = __hiloint2double((int)xh, 0);
+    // Predicated loads, unconditional FMAs: a null record issues no shared-memory wavefront, keeps whatever finite
+    // table values its landing registers held, and adds 0 * value.  (An `if` around loads and FMAs is compiled to
+    // a branch, which serialises consecutive slots on the load latency.)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "setp.ne.u32 p, %4, 0;\n\t"
+        VB_SEG_SETP4
         "@p ld.shared.v2.f64 {%0, %1}, [%5];\n\t"
         "@p ld.shared.v2.f64 {%2, %3}, [%6];\n\t}"
         : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3])
-        : "r"(c), "r"(addr), "r"(addr ^ 64u));
+        : "r"(xh), "r"(addr), "r"(addr ^ 64u));
     a[0] = fma(d, v[0], a[0]);
     a[1] = fma(d, v[1], a[1]);
     a[2] = fma(d, v[2], a[2]);
     a[3] = fma(d, v[3], a[3]);
 }
 // FP64 tables with 8 columns (n_donor <= 8): rows of 64 bytes, 4 lanes x 2 columns, one 16-byte load per lane.
-template <bool HI, bool WRAP>
-__device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes, double (&a)[2],
-                                         double (&v)[2]) {
-    const uint32_t c = HI ? (w & 0x001f0000u) : (w & 0x1fu);
-    uint32_t t;
-    asm("and.b32 %0, %1, %2;" : "=r"(t) : "r"(w), "r"(HI ? 0xffe00000u : 0xffe0u));
-    uint32_t off = HI ? __umulhi(t, 1u << 17) : t * 2u;    // row offset * 64 bytes
-    if (WRAP && off >= wrap_at) off -= ring_bytes;
-    const uint32_t addr = base + off;
-    const double d = __hiloint2double(0x43300000, (int)c) - 4503599627370496.0;
+__device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, double (&a)[2], double (&v)[2]) {
+    const uint32_t xh = w << 16;
+    const uint32_t addr = (w >> 10) + base;
+    const double d = __hiloint2double((int)xh, 0);
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "setp.ne.u32 p, %2, 0;\n\t"
+        VB_SEG_SETP2
         "@p ld.shared.v2.f64 {%0, %1}, [%3];\n\t}"
         : "+d"(v[0]), "+d"(v[1])
-        : "r"(c), "r"(addr));
+        : "r"(xh), "r"(addr));
     a[0] = fma(d, v[0], a[0]);
     a[1] = fma(d, v[1], a[1]);
 }
-// Fixed point: exact integer accumulation of count * value.  The upper record of a word is used in place
-// (count << 16, row offset << 16): the accumulators of odd slots carry a factor 2^16 that the epilogue removes
-// (safe while the reads of one owner stay below 2^16, checked when the format is built).
-template <bool HI, bool WRAP>
-__device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes, unsigned long long (&a)[4]) {
-    const uint32_t c = HI ? (w & 0x001f0000u) : (w & 0x1fu);
-    // the address does not depend on the null test: keeping it outside shortens the dependent chain in front of the load
-    uint32_t t;
-    asm("and.b32 %0, %1, %2;" : "=r"(t) : "r"(w), "r"(HI ? 0xffe00000u : 0xffe0u));
-    uint32_t off = HI ? __umulhi(t, 1u << 17) : t * 2u;    // row offset * 64 bytes
-    if (WRAP && off >= wrap_at) off -= ring_bytes;
-    const uint32_t addr = base + off;
+// Fixed point: exact integer accumulation of count * value.
+__device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, unsigned long long (&a)[4]) {
+    const uint32_t c = w & 0xffffu;
+    const uint32_t addr = (w >> 10) + base;
     if (c) {
         uint32_t v0, v1, v2, v3;
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
@@ -600,61 +716,37 @@ __device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, uint32_t wra
     }
 }
 
-template <bool WRAP>
-__device__ __forceinline__ void seg_super_step(const uint2& u, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes, double (&acc)[4][4],
-                                               SegScratch64& sc) {
-    seg_step<false, WRAP>(u.x, base, wrap_at, ring_bytes, acc[0], sc.v[0]); seg_step<true, WRAP>(u.x, base, wrap_at, ring_bytes, acc[1], sc.v[1]);
-    seg_step<false, WRAP>(u.y, base, wrap_at, ring_bytes, acc[2], sc.v[0]); seg_step<true, WRAP>(u.y, base, wrap_at, ring_bytes, acc[3], sc.v[1]);
+// the two halves of a super-step: slots 0, 1 and slots 2, 3 of the lane group
+template <int H>
+__device__ __forceinline__ void seg_half_step(uint32_t w0, uint32_t w1, uint32_t base, double (&acc)[4][4], SegScratch64& sc) {
+    seg_step(w0, base, acc[2 * H], sc.v[0]); seg_step(w1, base, acc[2 * H + 1], sc.v[1]);
 }
-template <bool WRAP>
-__device__ __forceinline__ void seg_super_step(const uint2& u, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes, double (&acc)[4][2],
-                                               SegScratchN& sc) {
-    seg_step<false, WRAP>(u.x, base, wrap_at, ring_bytes, acc[0], sc.v[0]); seg_step<true, WRAP>(u.x, base, wrap_at, ring_bytes, acc[1], sc.v[1]);
-    seg_step<false, WRAP>(u.y, base, wrap_at, ring_bytes, acc[2], sc.v[0]); seg_step<true, WRAP>(u.y, base, wrap_at, ring_bytes, acc[3], sc.v[1]);
+template <int H>
+__device__ __forceinline__ void seg_half_step(uint32_t w0, uint32_t w1, uint32_t base, double (&acc)[4][2], SegScratchN& sc) {
+    seg_step(w0, base, acc[2 * H], sc.v[0]); seg_step(w1, base, acc[2 * H + 1], sc.v[1]);
 }
-template <bool WRAP>
-__device__ __forceinline__ void seg_super_step(const uint2& u, uint32_t base, uint32_t wrap_at, uint32_t ring_bytes,
-                                               unsigned long long (&acc)[4][4], SegScratch32&) {
-    seg_step<false, WRAP>(u.x, base, wrap_at, ring_bytes, acc[0]); seg_step<true, WRAP>(u.x, base, wrap_at, ring_bytes, acc[1]);
-    seg_step<false, WRAP>(u.y, base, wrap_at, ring_bytes, acc[2]); seg_step<true, WRAP>(u.y, base, wrap_at, ring_bytes, acc[3]);
+template <int H>
+__device__ __forceinline__ void seg_half_step(uint32_t w0, uint32_t w1, uint32_t base, unsigned long long (&acc)[4][4], SegScratch32&) {
+    seg_step(w0, base, acc[2 * H]); seg_step(w1, base, acc[2 * H + 1]);
 }
 
-// the super-steps of one segment; the queue q holds the next DEPTH super-steps of the stream
-template <bool WRAP, int DEPTH, typename chunk_t, typename acc_t, typename scratch_t>
-__device__ __forceinline__ void seg_segment(uint32_t n, chunk_t (&q)[DEPTH], const unsigned char*& sp, uint32_t base, uint32_t wrap_at,
-                                            uint32_t ring_bytes, acc_t& acc, scratch_t& sc) {
-    for (uint32_t s = 0; s < n; s += DEPTH) {
-        // a group consumes DEPTH * 64 bytes of the warp's stream: one L2 prefetch per 128-byte line of it
-#pragma unroll
-        for (int l = 0; l < DEPTH * (VB_SEG_OWNERS * 2); l += 128)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + VB_SEG_L2_AHEAD + l));
-#pragma unroll
-        for (int i = 0; i < DEPTH; ++i) {
-            const chunk_t c = q[i];
-            q[i] = __ldcs(reinterpret_cast<const chunk_t*>(sp + i * (VB_SEG_OWNERS * 2)));
-            if (s + i < n) seg_super_step<WRAP>(c, base, wrap_at, ring_bytes, acc, sc);
-        }
-        sp += DEPTH * (VB_SEG_OWNERS * 2);
-    }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void lds64(uint32_t addr, uint32_t& a, uint32_t& b) {
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
 }
 
-// wait for a phase of a window barrier; with a suspend-time hint a waiting warp stays off the issue slots longer
-__device__ __forceinline__ void seg_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
-    if (hint_ns == 0) { mbar_wait(bar, parity); return; }
-    uint32_t ok;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
-    } while (!ok);
-}
-
-template <int PREC, int DEPTH>
+// 23 warps per SM leave 80 registers per lane (registers are handed out in units of 512 per warp: 88 would count as 96)
+template <int PREC>
 __global__ void __launch_bounds__((VB_SEG_MAX_WARPS + 1) * 32, 1)
 k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     using Cfg = SegCfg<PREC>;
-    constexpr int LPO = Cfg::LPO, M = Cfg::LPO, NC = Cfg::NC, ROWB = Cfg::ROWB;
+    constexpr int LPO = Cfg::LPO, M = Cfg::LPO, NC = Cfg::NC, ROWB = Cfg::ROWB, CH = VB_SEG_DEPTH;
+    constexpr uint32_t CHB = CH * VB_SEG_OWNERS * 4;             // bytes of a record chunk
     typedef typename std::conditional<PREC == 1, unsigned long long, double>::type acc_t;
-    typedef uint2 chunk_t;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int b = blockIdx.y;
     if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
@@ -665,12 +757,14 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     }
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int NW = sa.nwarps, NB = sa.nb;
+    const int NW = sa.nwarps, NB = sv.nb;
     const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
     const uint32_t win_bytes = (uint32_t)sv.win_rows * ROWB;
-    const uint32_t ring = smem_u32(smem);
-    const uint32_t bars = ring + (uint32_t)NB * win_bytes;        // full[NB] then empty[NB]
-    double* red = reinterpret_cast<double*>(smem + (size_t)NB * win_bytes + 16 * 8);
+    // dynamic shared memory: full[NB] and empty[NB] window barriers, two record-chunk barriers per consumer warp, the
+    // block-reduction scratch, (4 KB in) the window ring, and behind it two record chunks per consumer warp
+    const uint32_t bars = smem_u32(smem);                         // warp-uniform: lives in the uniform register file
+    const uint32_t ring = bars + VB_SG_RING_OFF;
+    double* red = reinterpret_cast<double*>(smem + VB_SG_RED_OFF);
 
     // tasks are dealt to CTAs in boustrophedon order of the sorted list: warp ww of CTA c serves task
     // ww * grid + (ww odd ? grid - 1 - c : c), so every CTA gets the same mix of long and short tasks
@@ -682,6 +776,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < NB; ++i) { mbar_init(bars + 8 * i, 1); mbar_init(bars + 8 * (NB + i), nstream > 0 ? nstream : 1); }
+        for (int i = 0; i < 2 * NW; ++i) mbar_init(bars + VB_SG_RECBAR_OFF + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -700,14 +795,16 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
             int bi = 0;
             uint32_t use = 0;                               // how often buffer bi has been filled before
             for (int wd = 0; wd < sv.n_win; ++wd) {
+#ifndef VB_SEG_DIAG_NOSYNC
                 if (use > 0) mbar_wait(bars + 8 * (NB + bi), (use - 1) & 1);      // every consumer released the previous fill
+#endif
 #ifdef VB_SEG_CANARY
                 // Protocol canary (build.py variants "canary" / "plainfill"): a released buffer is overwritten with NaNs
                 // before it is refilled.  A consumer that read a row before its window's fill had completed, or after it
                 // had released the window, would pick up a NaN, which no later step can remove from its sums -- so
                 // NaN-free, bit-identical results under this build show that no such access happens.
                 {
-                    unsigned long long* dst = reinterpret_cast<unsigned long long*>(smem + (size_t)bi * win_bytes);
+                    unsigned long long* dst = reinterpret_cast<unsigned long long*>(smem + VB_SG_RING_OFF + (size_t)bi * win_bytes);
                     for (uint32_t e = lane; e < win_bytes / 8; e += 32) dst[e] = 0x7ff8dead0000beefull;
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // before the bulk copies overwrite it
                     __syncwarp();
@@ -723,7 +820,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
                     const int64_t rows = sv.n_gather - r0 < sv.win_rows ? sv.n_gather - r0 : sv.win_rows;
                     const uint32_t n16 = (uint32_t)(rows * ROWB / 16);
                     const uint4* src = reinterpret_cast<const uint4*>(T + (size_t)r0 * ROWB);
-                    uint4* dst = reinterpret_cast<uint4*>(smem + (size_t)bi * win_bytes);
+                    uint4* dst = reinterpret_cast<uint4*>(smem + VB_SG_RING_OFF + (size_t)bi * win_bytes);
                     for (uint32_t e = lane; e < n16; e += 32) dst[e] = __ldg(src + e);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bars + 8 * bi);
@@ -746,10 +843,19 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
                 __syncwarp();
                 if (++bi == NB) { bi = 0; ++use; }
             }
+            // a warp that advances near the end of the table waits for windows past it: complete their barriers empty
+            for (int wd = 0; wd < sv.span; ++wd) {
+#ifndef VB_SEG_DIAG_NOSYNC
+                if (use > 0) mbar_wait(bars + 8 * (NB + bi), (use - 1) & 1);
+#endif
+                if (lane == 0) mbar_arrive(bars + 8 * bi);
+                __syncwarp();
+                if (++bi == NB) { bi = 0; ++use; }
+            }
         }
     } else if (task >= 0) {
         // ---------------- consumer warp: 32 owner slots, LPO lanes per slot
-        const unsigned char* sp = reinterpret_cast<const unsigned char*>(sv.rec) + (size_t)sv.task_off[task] * (VB_SEG_OWNERS * 2) + g * (M * 2);
+        const int64_t s0 = sv.task_off[task], s1 = sv.task_off[task + 1];
         typename std::conditional<PREC == 0, SegScratch64, typename std::conditional<PREC == 1, SegScratch32, SegScratchN>::type>::type sc;
         if constexpr (PREC == 0) {
 #pragma unroll
@@ -759,36 +865,70 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) sc.v[i >> 1][i & 1] = 0.0;
         }
-        chunk_t q[DEPTH];
-#pragma unroll
-        for (int i = 0; i < DEPTH; ++i) q[i] = __ldcs(reinterpret_cast<const chunk_t*>(sp + i * (VB_SEG_OWNERS * 2)));
-        sp += DEPTH * (VB_SEG_OWNERS * 2);
-        const uint16_t* __restrict__ ns = sv.nsteps + (size_t)task * sv.n_win;
-        uint32_t n_next = ns[0];
-        int bi = 0;                          // buffer of window wd
-        uint32_t phase = 0;                  // its fill parity
-        // FP64 rows: odd lane groups read the upper half of a row first (see seg_step)
-        const uint32_t lane_base = ring + (uint32_t)sub * 16 + (PREC == 0 ? (uint32_t)(g & 1) * 64 : 0u);
-        const uint32_t ring_bytes = (uint32_t)NB * win_bytes;
-        const int look = sv.look;
-        const uint32_t hint = (uint32_t)sa.wait_hint_ns;
-        if (look) seg_wait(bars, 0, hint);   // window 0; every segment then waits for the window after its own
-        for (int wd = 0; wd < sv.n_win; ++wd) {
-            const uint32_t n = n_next;
-            if (wd + 1 < sv.n_win) n_next = ns[wd + 1];
-            const bool last_buf = bi + 1 == NB;
-            if (look) {
-                if (wd + 1 < sv.n_win) seg_wait(bars + 8 * (last_buf ? 0 : bi + 1), last_buf ? phase ^ 1 : phase, hint);
-            } else {
-                seg_wait(bars + 8 * bi, phase, hint);
+        // this lane's granule of ring row 0, minus the constant upper bits of the count code (see seg_step); FP64
+        // rows: odd lane groups read the upper half of a row first
+        uint32_t base = ring + (uint32_t)sub * 16 + (PREC == 0 ? (uint32_t)(g & 1) * 64 : 0u) - (PREC == 0 ? 32u : (PREC == 2 ? 16u : 0u));
+        asm volatile("" : "+r"(base));
+        const int span = sv.span;
+        // The warp holds `span` consecutive windows.  rs: buffer of the oldest one, with the fill parity of that buffer's
+        // current window in bit 31.  An advance releases the oldest window and waits for the one behind the newest.
+#ifndef VB_SEG_DIAG_NOSYNC
+        for (int wd = 0; wd < span; ++wd) mbar_wait(bars + 8 * wd, 0);
+#endif
+        uint32_t rs = 0;
+        auto advance = [&]() {
+            __syncwarp();                                 // every lane's reads of the oldest window are done
+            const uint32_t ri = rs & 0xffffu;
+            uint32_t ni = ri + (uint32_t)span, np = rs >> 31;
+            if (ni >= (uint32_t)NB) { ni -= (uint32_t)NB; np ^= 1u; }
+#ifndef VB_SEG_DIAG_NOSYNC     // timing diagnostic (build.py variant "nosync"): no window hand-over at all
+            if (lane == 0) mbar_arrive(bars + 8 * ((uint32_t)NB + ri));
+            mbar_wait(bars + 8 * ni, np);
+#endif
+            if ((++rs & 0xffffu) == (uint32_t)NB) rs = (rs & 0x80000000u) ^ 0x80000000u;
+        };
+        // The record stream of the task arrives in chunks of CH super-steps (512 bytes), bulk-copied into this warp's
+        // two chunk buffers two chunks ahead of their use: a record costs the warp one shared-memory load and no
+        // register queue.  Chunk gi sits in buffer gi & 1; its barrier completes with parity (gi >> 1) & 1.
+        const int ngroups = (int)((s1 - s0) / CH);
+        const uint32_t chunk0 = (uint32_t)(s0 / CH);             // chunk index in the whole stream (512-byte units)
+        const unsigned char* grec = reinterpret_cast<const unsigned char*>(sv.rec);
+        const uint32_t rbuf = ring + (uint32_t)NB * win_bytes + (uint32_t)w * (2 * CHB);
+        const uint32_t rbar = bars + VB_SG_RECBAR_OFF + (uint32_t)w * 16;
+        if (lane == 0) {
+            for (int j = 0; j < 2 && j < ngroups; ++j) {
+                mbar_expect_tx(rbar + 8 * j, CHB);
+                bulk_g2s(rbuf + j * CHB, grec + (size_t)(chunk0 + j) * CHB, CHB, rbar + 8 * j);
             }
-            const uint32_t base = lane_base + (uint32_t)bi * win_bytes;
-            if (look && last_buf) seg_segment<true, DEPTH>(n, q, sp, base, win_bytes, ring_bytes, acc, sc);
-            else seg_segment<false, DEPTH>(n, q, sp, base, win_bytes, ring_bytes, acc, sc);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + 8 * (NB + bi));
-            if (last_buf) { bi = 0; phase ^= 1; } else ++bi;
         }
+        for (int gi = 0; gi < ngroups; ++gi) {
+            const uint32_t buf = (uint32_t)gi & 1u;
+            mbar_wait(rbar + 8 * buf, ((uint32_t)gi >> 1) & 1u);
+            uint32_t cb = rbuf + buf * CHB + (uint32_t)g * 16;
+            asm volatile("" : "+r"(cb));                         // one register per chunk, not recomputed per load
+            uint4 c = lds128(cb);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const uint32_t adv = c.x >> 28;
+                if (adv) {
+                    uint32_t a = adv;
+                    do advance(); while (--a);
+                    c.x &= 0x0fffffffu;
+                }
+                // the records of the next super-step are loaded half by half as soon as this one's are decoded
+                seg_half_step<0>(c.x, c.y, base, acc, sc);
+                if (i + 1 < CH) lds64(cb + (i + 1) * (VB_SEG_OWNERS * 4), c.x, c.y);
+                seg_half_step<1>(c.z, c.w, base, acc, sc);
+                if (i + 1 < CH) lds64(cb + (i + 1) * (VB_SEG_OWNERS * 4) + 8, c.z, c.w);
+            }
+            __syncwarp();                                 // every lane has read the chunk: refill its buffer
+            if (lane == 0 && gi + 2 < ngroups) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(rbar + 8 * buf, CHB);
+                bulk_g2s(rbuf + buf * CHB, grec + (size_t)(chunk0 + (uint32_t)gi + 2u) * CHB, CHB, rbar + 8 * buf);
+            }
+        }
+        for (int a = sv.tail[task]; a > 0; --a) advance();       // release the windows still held
     }
 
     // ---------------- epilogue: the LPO lanes of a slot hold NC columns each
@@ -804,8 +944,8 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     const int col0 = PREC == 0 ? 2 * sub + 8 * (g & 1) : (PREC == 1 ? 4 * sub : 2 * sub);
     const int col2 = PREC == 0 ? ((g & 1) ? -8 : 8) : 2;
     const int RW = PREC == 2 ? 8 : VB_ROW_DOUBLES;
-    const double unq = PREC != 1 ? 1.0 : (sa.mode == GM_SNP ? 1.0 / 4294967295.0 : -1.0 / p.qscale[b]);
-    const double unq_hi = unq / 65536.0;     // odd slots accumulate count << 16 (exact power of two in either precision)
+    // FP64 tables: the records carry 2 * count;  fixed point: undo the table scale
+    const double unq = PREC != 1 ? 0.5 : (sa.mode == GM_SNP ? 1.0 / 4294967295.0 : -1.0 / p.qscale[b]);
 
     // the streaming task first, then a share of the tasks without records (accumulators are zero for those)
     int64_t et = task;
@@ -822,7 +962,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
             const int owner = sv.perm[et * VB_SEG_OWNERS + g * M + mi];
             double v[NC];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) v[c] = (double)acc[mi][c] * ((mi & 1) ? unq_hi : unq);
+            for (int c = 0; c < NC; ++c) v[c] = (double)acc[mi][c] * unq;
             bool valid[NC], primary[NC];
             int kk[NC];
 #pragma unroll
@@ -983,14 +1123,16 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
 static SegView view_of_set(const SegSet& g) {
     SegView v;
     v.n_owner = g.n_owner; v.n_gather = g.n_gather; v.n_task = g.n_task; v.n_task_stream = g.n_task_stream;
-    v.n_win = g.n_win; v.win_rows = g.win_rows; v.look = g.look;
-    v.perm = g.perm; v.nsteps = g.nsteps; v.task_off = g.task_off; v.rec = g.rec;
+    v.n_win = g.n_win; v.win_rows = g.win_rows; v.nb = g.nb; v.span = g.span;
+    v.perm = g.perm; v.task_off = g.task_off; v.tail = g.tail; v.rec = g.rec;
     v.hptr = g.hptr; v.hrow = g.hrow; v.hcnt = g.hcnt;
     return v;
 }
 
 static size_t seg_smem(int prec, int nb, int win_rows) {
-    return (size_t)nb * win_rows * (prec == 0 ? 128 : 64) + 16 * 8 + (size_t)(VB_SEG_MAX_WARPS + 1) * VB_SG_RED_DOUBLES * 8;
+    static_assert(2 * VB_SEG_MAX_NB * 8 <= VB_SG_RECBAR_OFF && VB_SG_RECBAR_OFF + VB_SEG_MAX_WARPS * 16 <= VB_SG_RED_OFF &&
+                  VB_SG_RED_OFF + (VB_SEG_MAX_WARPS + 1) * VB_SG_RED_DOUBLES * 8 <= VB_SG_RING_OFF, "shared-memory layout of k_seg");
+    return VB_SG_RING_OFF + (size_t)nb * win_rows * (prec == 0 ? 128 : 64) + (size_t)VB_SEG_MAX_WARPS * 2 * VB_SEG_DEPTH * VB_SEG_OWNERS * 4;
 }
 
 static bool g_seg_attr_set[64] = {false};     // per device: function attributes belong to the context
@@ -1019,8 +1161,7 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
             }
             if (fa.sharedSizeBytes > st_max) st_max = fa.sharedSizeBytes;
         };
-        opt_in((const void*)k_seg<0, 4>); opt_in((const void*)k_seg<1, 4>); opt_in((const void*)k_seg<0, 8>);
-        opt_in((const void*)k_seg<2, 4>); opt_in((const void*)k_seg<1, 8>);
+        opt_in((const void*)k_seg<0>); opt_in((const void*)k_seg<1>); opt_in((const void*)k_seg<2>);
         if (rc_attr) return rc_attr;
         g_seg_static[dev_slot] = st_max;
         g_seg_attr_set[dev_slot] = true;
@@ -1031,7 +1172,7 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
     const SegView sv = view_of_set(g);
     SegArgs sa;
     memset(&sa, 0, sizeof(sa));
-    sa.mode = mode; sa.theta_mode = theta_mode; sa.nb = nb;
+    sa.mode = mode; sa.theta_mode = theta_mode;
     const double* tab64 = ori ? p.RP : p.Wt;
     if (prec != 1) { sa.table = reinterpret_cast<const unsigned char*>(tab64); sa.table_stride = g.n_gather * (prec == 0 ? 128 : 64); }
     else { sa.table = reinterpret_cast<const unsigned char*>(ori ? p.RPq : p.Wq); sa.table_stride = g.n_gather * 64; }
@@ -1040,8 +1181,6 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
         if (!plain || prec == 1 || ori != 0) { vb_set_error("plain segment pass: bad arguments"); return VB_E_ARG; }
         sa.plain_out = plain->out; sa.plain_ld = plain->ld; sa.plain_off = plain->off; sa.plain_cols = plain->cols;
     }
-    static const int wait_hint = env_int("VIREO_B200_SEG_WAIT_NS", 0);
-    sa.wait_hint_ns = wait_hint;
     int grid_x;
     vb_seg_geometry(g, &grid_x, &sa.nwarps);
     const int cls = ori ? 0 : 3;
@@ -1056,11 +1195,9 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
     const dim3 grid(grid_x, p.B);
     const int threads = (sa.nwarps + 1) * 32;
     VB_LAUNCH(cls, st, {
-        if (prec == 2) k_seg<2, 4><<<grid, threads, smem, st>>>(sv, p, sa);
-        else if (prec == 0 && g.depth == 4) k_seg<0, 4><<<grid, threads, smem, st>>>(sv, p, sa);
-        else if (prec == 0) k_seg<0, 8><<<grid, threads, smem, st>>>(sv, p, sa);
-        else if (g.depth == 4) k_seg<1, 4><<<grid, threads, smem, st>>>(sv, p, sa);
-        else k_seg<1, 8><<<grid, threads, smem, st>>>(sv, p, sa);
+        if (prec == 2) k_seg<2><<<grid, threads, smem, st>>>(sv, p, sa);
+        else if (prec == 0) k_seg<0><<<grid, threads, smem, st>>>(sv, p, sa);
+        else k_seg<1><<<grid, threads, smem, st>>>(sv, p, sa);
     });
     VB_CUDA(cudaGetLastError());
     return VB_OK;
