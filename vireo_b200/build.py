@@ -30,7 +30,9 @@ VARIANTS = {"plainfill": ["-DVB_SEG_PLAIN_FILL", "-DVB_SEG_CANARY"], "canary": [
             # timing diagnostics of the segment kernels (results are garbage by design): no table loads / no window
             # synchronisation in the consumer warps / both
             "nolds": ["-DVB_SEG_DIAG_NOLDS"], "nosync": ["-DVB_SEG_DIAG_NOSYNC"],
-            "noldsnosync": ["-DVB_SEG_DIAG_NOLDS", "-DVB_SEG_DIAG_NOSYNC"]}
+            "noldsnosync": ["-DVB_SEG_DIAG_NOLDS", "-DVB_SEG_DIAG_NOSYNC"],
+            # window waits with the warp asleep between polls: producer only / producer and consumers
+            "sleepp": ["-DVB_SEG_SLEEP_P=256"], "sleeppc": ["-DVB_SEG_SLEEP_P=256", "-DVB_SEG_SLEEP_C=64"]}
 
 
 def up_to_date(lib=LIB):

@@ -442,12 +442,13 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
     }
     VB_CUDA(cudaStreamSynchronize(st));
 
-    // launch geometry: one CTA per SM, as few consumer warps as cover the streaming tasks
-    int nw = (int)((nts + sm - 1) / sm);
-    if (nw < 1) nw = 1;
-    if (nw > VB_SEG_MAX_WARPS) nw = VB_SEG_MAX_WARPS;
-    int64_t grid = (nts + nw - 1) / nw;
+    // launch geometry: one CTA on every SM when there are enough streaming tasks, as few consumer warps as cover them (the
+    // last, partly filled round of the deal holds the lightest tasks of the sorted list)
+    int64_t grid = nts < sm ? nts : sm;
     if (grid < 1) grid = 1;
+    int nw = (int)((nts + grid - 1) / grid);
+    if (nw < 1) nw = 1;
+    if (nw > VB_SEG_MAX_WARPS) { nw = VB_SEG_MAX_WARPS; grid = (nts + nw - 1) / nw; }
     if (grid > 65535 * 16) { vb_set_error("segment format: too many owner rows"); return VB_E_UNSUPPORTED; }
     g.grid = (int)grid; g.nwarps = nw;
     g.bytes = (int64_t)n_rec * 4 + n_task * VB_SEG_OWNERS * 4 + (nts + 1) * 8 + (O + 1) * 8 + g.n_heavy * 8;
@@ -623,6 +624,17 @@ __global__ void __launch_bounds__(VB_THREADS) k_seg_quant_rows(const double* __r
 // k_seg
 // ---------------------------------------------------------------------------------------------
 #define VB_SG_RED_DOUBLES (2 * VB_MAX_GT)
+// how the producer / the consumers wait for a window barrier (build.py variants "sleepp", "sleeppc")
+#ifdef VB_SEG_SLEEP_P
+#define VB_SEG_PWAIT(bar, par) mbar_wait_sleep(bar, par, VB_SEG_SLEEP_P)
+#else
+#define VB_SEG_PWAIT(bar, par) mbar_wait(bar, par)
+#endif
+#ifdef VB_SEG_SLEEP_C
+#define VB_SEG_CWAIT(bar, par) mbar_wait_sleep(bar, par, VB_SEG_SLEEP_C)
+#else
+#define VB_SEG_CWAIT(bar, par) mbar_wait(bar, par)
+#endif
 #define VB_SG_RECBAR_OFF 256u        // record-chunk barriers of the consumer warps (two each) behind the window barriers
 #define VB_SG_RED_OFF 1024u         // block-reduction scratch
 #define VB_SG_PIECE 16384u          // bytes per bulk copy
@@ -796,7 +808,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
             uint32_t use = 0;                               // how often buffer bi has been filled before
             for (int wd = 0; wd < sv.n_win; ++wd) {
 #ifndef VB_SEG_DIAG_NOSYNC
-                if (use > 0) mbar_wait(bars + 8 * (NB + bi), (use - 1) & 1);      // every consumer released the previous fill
+                if (use > 0) VB_SEG_PWAIT(bars + 8 * (NB + bi), (use - 1) & 1);   // every consumer released the previous fill
 #endif
 #ifdef VB_SEG_CANARY
                 // Protocol canary (build.py variants "canary" / "plainfill"): a released buffer is overwritten with NaNs
@@ -846,7 +858,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
             // a warp that advances near the end of the table waits for windows past it: complete their barriers empty
             for (int wd = 0; wd < sv.span; ++wd) {
 #ifndef VB_SEG_DIAG_NOSYNC
-                if (use > 0) mbar_wait(bars + 8 * (NB + bi), (use - 1) & 1);
+                if (use > 0) VB_SEG_PWAIT(bars + 8 * (NB + bi), (use - 1) & 1);
 #endif
                 if (lane == 0) mbar_arrive(bars + 8 * bi);
                 __syncwarp();
@@ -883,7 +895,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
             if (ni >= (uint32_t)NB) { ni -= (uint32_t)NB; np ^= 1u; }
 #ifndef VB_SEG_DIAG_NOSYNC     // timing diagnostic (build.py variant "nosync"): no window hand-over at all
             if (lane == 0) mbar_arrive(bars + 8 * ((uint32_t)NB + ri));
-            mbar_wait(bars + 8 * ni, np);
+            VB_SEG_CWAIT(bars + 8 * ni, np);
 #endif
             if ((++rs & 0xffffu) == (uint32_t)NB) rs = (rs & 0x80000000u) ^ 0x80000000u;
         };
@@ -922,6 +934,13 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
                 if (i + 1 < CH) lds64(cb + (i + 1) * (VB_SEG_OWNERS * 4) + 8, c.z, c.w);
             }
             __syncwarp();                                 // every lane has read the chunk: refill its buffer
+#ifdef VB_SEG_CANARY
+            // protocol canary: the released chunk is wiped (null records) before its refill; a lane that read it too
+            // late, or the next chunk too early, would lose pairs and change the results
+            for (uint32_t e = lane; e < CHB / 4; e += 32)
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(rbuf + buf * CHB + 4 * e), "r"(0u) : "memory");
+            __syncwarp();
+#endif
             if (lane == 0 && gi + 2 < ngroups) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(rbar + 8 * buf, CHB);
