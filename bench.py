@@ -376,6 +376,11 @@ def run_b200(args):
     # ---- restarts: every rank draws all inits in the reference's RNG order and keeps its share
     inits = draw_inits(w, n_init)
     mine = [i for i in range(n_init) if i % world == rank]
+    # this rank's input states live in pinned host memory (the contract's "host->device copy of that step's inputs from
+    # pinned host memory"): numpy views of page-locked blocks, handed to the public API like any other array
+    def pinned(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    inits = [(pinned(a), pinned(b)) if i in mine else (a, b) for i, (a, b) in enumerate(inits)]
     models = _new_models(vb, w, inits, mine)
 
     def reset_models():
@@ -678,7 +683,7 @@ def run_b200(args):
         "ms_per_iteration_per_restart": ms / args.steps / T_ITERS,
         "roofline": roofline, "kernels": kernels, "kernel_family": family, "fixed32": fixed32, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "vireo_b200.Vireo.fit(counts, None, ...): numpy state in, numpy results out, "
+                "steps": e2e_steps, "api": "vireo_b200.Vireo.fit(counts, None, ...): numpy state in (arrays in pinned host memory), numpy results out, "
                 "counts = vireo_b200.stage(AD, DP) staged to HBM once (staging_ms)",
                 "raw_matrices": {"value": world * R * T_ITERS / raw_s, "unit": "it/s",
                                  "api": "Vireo.fit(AD, DP) with the scipy matrices: the staged copy is re-used after a "
