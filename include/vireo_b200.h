@@ -108,14 +108,14 @@ int vb_binom_const(const vb_counts* m, double* scratch, double* out_host, void* 
 /* Sizes of the per-call workspaces, in elements, for a batch of B restarts. */
 typedef struct vb_ws_sizes {
     int64_t S;        /* doubles: S1 and S2, each [B, n_var, K]                 */
-    int64_t W;        /* doubles: per-allele tables [B, n_var, 2, K] (gather / segment paths: K -> 16; + fixed-point copy) */
+    int64_t W;        /* doubles: per-allele tables [B, n_var, 2, K] (segment kernels: rows of 16 or 8 columns; + fixed-point copy) */
     int64_t loglik;   /* doubles: [B, n_cell, K]                               */
     int64_t ab;       /* doubles: [B, T, 2*G] digamma differences              */
     int64_t part;     /* doubles: block partial sums                           */
     int64_t scal;     /* doubles: [B, 8] ELBO terms                            */
     int64_t ctrl;     /* int32:   [B, 8] {done, it_next, last_it, n_decrease, 3 tickets of fused tails, -} */
-    int64_t rpad;     /* doubles: ID_prob in 128-byte rows [B, n_cell, 16] (gather path, else 0) */
-    int64_t heavy;    /* doubles: residual sums [B, max(n_cell, 2 n_var), 16] (gather path, else 0) */
+    int64_t rpad;     /* doubles: ID_prob in 128-byte rows [B, n_cell, 16] (segment kernels, else 0) */
+    int64_t heavy;    /* doubles: residual sums [B, max(n_cell, 2 n_var), 16] (segment kernels, else 0) */
 } vb_ws_sizes;
 
 typedef struct vb_vireo_args {
@@ -144,7 +144,7 @@ typedef struct vb_vireo_args {
     int32_t* ctrl;
     /* outputs */
     double* elbo;                /* [B, max_iter] every computed ELBO (the reference returns ELBO[:it]) */
-    /* gather-path workspace (may be NULL when vb_vireo_ws_sizes reports 0) */
+    /* segment-kernel workspace (may be NULL when vb_vireo_ws_sizes reports 0) */
     double *rpad, *heavy;
     /* element counts of the workspaces as the caller allocated them (copy of what vb_vireo_ws_sizes returned):
      * every entry point checks them against what the kernel family it is about to launch needs and fails with
@@ -194,7 +194,7 @@ typedef struct vb_bmm_args {
     double *S1, *S2, *W, *loglik, *part, *scal;
     int32_t* ctrl;
     double* elbo;                /* [B, max_iter]                                                     */
-    double *rpad, *heavy;        /* gather-path workspace (may be NULL when vb_bmm_ws_sizes reports 0) */
+    double *rpad, *heavy;        /* segment-kernel workspace (may be NULL when vb_bmm_ws_sizes reports 0) */
     vb_ws_sizes ws;              /* allocated element counts, checked like vb_vireo_args.ws */
 } vb_bmm_args;
 

@@ -1014,9 +1014,11 @@ static bool rows_lane_ok(int K, int64_t nnz, int64_t n_row) {
     return mode == 2 || nnz >= 160 * (n_row > 0 ? n_row : 1);
 }
 
-// VIREO_B200_LANE_DEEP=0: half the records per lane and round, twice the warps per SM
+// records per lane and round of the lane kernels: 2 (K <= 4) / 1 (K <= 8) by default; VIREO_B200_LANE_DEEP=1 doubles
+// them at half the warps per SM (measured slower on the matrices these kernels serve: cfg2 15.7k -> 17.5k it/s,
+// cfg5 40 -> 36 ms per BinomMixtureVB.fit call with the shallow variant)
 static bool lane_deep() {
-    static const bool on = !(getenv("VIREO_B200_LANE_DEEP") && atoi(getenv("VIREO_B200_LANE_DEEP")) == 0);
+    static const bool on = getenv("VIREO_B200_LANE_DEEP") && atoi(getenv("VIREO_B200_LANE_DEEP")) != 0;
     return on;
 }
 
