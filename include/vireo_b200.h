@@ -88,7 +88,10 @@ int vb_counts_slice(const vb_counts* m, int64_t cell_begin, int64_t cell_end, vo
  * 8 residual pairs, 9 stream pairs};
  * 60: why the automatic selector last served this matrix with the row kernels: 0 it did not, 1 small matrix
  *     (by design), 2 building the segment formats FAILED (vb_counts_note has the message; the row kernels are
- *     several times slower on large matrices), 3 residual-dominated counts (by design), 4 n_donor > 16 */
+ *     several times slower on large matrices), 3 residual-dominated counts (by design), 4 n_donor > 16;
+ * 61: launches of the row-split cell pass (0: not in use): when a matrix has few cells for the SMs of the device but a
+ *     long table (one rank's share of a cell-sharded fit, GT-given fits on mid-sized data) the table rows of the cell
+ *     pass are cut into that many ranges that run side by side and a finish kernel adds their partial sums */
 int64_t vb_counts_info(const vb_counts* m, int what);
 /* message of the failed format build behind vb_counts_info(m, 60) == 2 ("" otherwise) */
 const char* vb_counts_note(const vb_counts* m);

@@ -34,6 +34,13 @@ def step():
 for _ in range(2):
     step()
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(3):
+    step()
+e1.record()
+torch.cuda.synchronize()
+ms_iter = e0.elapsed_time(e1) / 3 / iters
 _lib.load().vb_profile_enable(1)
 step()
 torch.cuda.synchronize()
@@ -41,6 +48,6 @@ prof = _lib.profile_read()
 _lib.load().vb_profile_enable(0)
 info = {k: int(_lib.load().vb_counts_info(local.handle, 20 + i)) for i, k in enumerate(
     ["built", "steps_cell", "steps_snp", "reads_cell", "reads_snp", "grid_cell", "grid_snp", "bytes", "residual", "stream_pairs"])}
-print(json.dumps({"shards": n, "cells": c1 - c0, "kernels_ms": {k: round(v[0] / v[1], 4) for k, v in prof.items() if v[1]},
+print(json.dumps({"shards": n, "cells": c1 - c0, "ms_per_iteration": round(ms_iter, 4), "split": int(_lib.load().vb_counts_info(local.handle, 61)), "kernels_ms": {k: round(v[0] / v[1], 4) for k, v in prof.items() if v[1]},
                   "fill": {"cell": round(info["stream_pairs"] / max(1, 32 * info["steps_cell"]), 4),
                            "snp": round(info["stream_pairs"] / max(1, 32 * info["steps_snp"]), 4)}, "format": info}))

@@ -318,3 +318,45 @@ def test_segment_format_holds_every_pair_exactly_once(vb, shape):
             _lib.check(lib.vb_seg_verify(counts.handle, kind, ori, out))
             assert out[0] == n_pairs, (kind, ori, list(out), n_pairs)
             assert out[1] == 0, "format kind %d pass %d: %d errors %s" % (kind, ori, out[1], list(out))
+
+
+def test_row_split_cell_pass_vs_oracle(vb):
+    """Few cells, many SNPs (2000 x 20000 x 16): the cell pass of the window-segment family cuts the table rows into
+    ranges that run side by side and adds their partial sums in a finish kernel (vb_counts_info 61 = launches in use).
+    Free-running fits against the oracle: learn-GT from the reference's random start, and GT-given."""
+    from vireo_b200 import _lib
+    C, V, K = 2000, 20000, 16
+    AD, DP, donor, GT = O.synth_counts(C, V, K, density=0.02, seed=11)
+    kw = dict(max_iter=8, min_iter=8, delay_fit_theta=2, verbose=False)
+    _lib.set_path("seg")
+    try:
+        counts = vb.stage(AD, DP)
+        np.random.seed(3)
+        m = vb.Vireo(n_cell=C, n_var=V, n_donor=K)
+        o = O.vireo_new(C, V, K, ID_prob_init=m.ID_prob.copy(), GT_prob_init=m.GT_prob.copy())
+        o.ID_prob, o.GT_prob = m.ID_prob.copy(), m.GT_prob.copy()
+        elbo = _quiet(m._fit_VB, counts, None, **kw)
+        assert int(_engine_info(vb, counts, 61)) >= 2, "row-split cell pass not in use"
+        elbo_o = _quiet(O.vireo_fit_vb, o, AD, DP, **kw)
+        rel_close(elbo, elbo_o, E_TOL, "ELBO")
+        rel_close(m.ID_prob, o.ID_prob, P_TOL, "ID_prob")
+        rel_close(m.GT_prob, o.GT_prob, P_TOL, "GT_prob")
+        assert np.array_equal(m.ID_prob.argmax(1), o.ID_prob.argmax(1))
+
+        prior = np.full((V, K, 3), 0.01)
+        np.put_along_axis(prior, np.asarray(GT)[:, :, None], 0.98, axis=2)
+        np.random.seed(4)
+        m = vb.Vireo(n_cell=C, n_var=V, n_donor=K, learn_GT=False, GT_prob_init=prior.copy())
+        m.set_prior(GT_prior=prior.copy())
+        o = O.vireo_new(C, V, K, learn_GT=False, GT_prob_init=prior.copy(), ID_prob_init=m.ID_prob.copy())
+        O.vireo_set_prior(o, GT_prior=prior.copy())
+        o.ID_prob = m.ID_prob.copy()
+        elbo = _quiet(m._fit_VB, counts, None, **kw)
+        elbo_o = _quiet(O.vireo_fit_vb, o, AD, DP, **kw)
+        rel_close(elbo, elbo_o, E_TOL, "ELBO (GT given)")
+        rel_close(m.ID_prob, o.ID_prob, P_TOL, "ID_prob (GT given)")
+        assert np.array_equal(m.ID_prob.argmax(1), o.ID_prob.argmax(1))
+        assert (m.ID_prob.argmax(1) == donor).mean() > 0.99
+    finally:
+        _lib.set_path("auto")
+        vb.clear_cache()

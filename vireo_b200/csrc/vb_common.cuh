@@ -88,6 +88,20 @@ struct SegView {
     const uint32_t* __restrict__ hcnt;
 };
 
+// Row-split cell pass (vb_seg.cu): when a matrix has few owner tasks for the SMs of the device but a long table (one
+// rank's share of a cell-sharded fit, GT-given fits on mid-sized data), the table rows are cut into R ranges with one
+// segment format each; the R launches run side by side on R streams, every CTA streams 1/R of the table, and a small
+// kernel adds the partial sums and finishes the cell update.
+#define VB_SEG_MAX_SPLIT 8
+struct SegSplit {
+    int R;                                  // 0: not built / not in use
+    int failed;
+    SegSet set[VB_SEG_MAX_SPLIT];
+    int64_t row_lo[VB_SEG_MAX_SPLIT + 1];   // table rows [row_lo[r], row_lo[r+1]) belong to range r
+    cudaStream_t aux[VB_SEG_MAX_SPLIT];
+    cudaEvent_t fork, join[VB_SEG_MAX_SPLIT];
+};
+
 struct vb_counts {
     int device;
     int sm_count;
@@ -107,6 +121,7 @@ struct vb_counts {
     // of 64 B (16 columns), 2 FP64 rows of 64 B (8 columns, n_donor <= 8)
     SegSet sA[3];           // cell pass
     SegSet sB[3];           // SNP pass
+    SegSplit rA[3];         // cell pass, table rows split over R launches
     int seg_failed[3];
     // why the automatic selector last chose the row kernels for this matrix: 0 it did not, 1 small matrix (the passes
     // are launch/latency bound either way), 2 building the segment formats failed (message kept in seg_error),
@@ -134,6 +149,7 @@ void vb_seg_free(vb_counts* m);
 // what the kernels see of the staged counts
 struct CountsView {
     int64_t C, V, N;
+    int64_t g_lo, g_hi;        // segment-format builders: only pairs with a gather row in [g_lo, g_hi), rebased to g_lo
     const int64_t* __restrict__ cell_ptr;
     const int32_t* __restrict__ cell_idx;
     const uint32_t* __restrict__ cell_cnt;
@@ -265,8 +281,13 @@ int vb_pad_rows_launch(const vb_counts* m, const double* src, int64_t n_row, int
                        cudaStream_t st);
 enum { GM_CELL = 0, GM_CELL_LL = 1, GM_SNP = 2, GM_PLAIN = 3 };
 void vb_seg_geometry(const SegSet& g, int* grid, int* nwarps);
-struct SegPlain { double* out; int64_t ld; int off, cols; };       // GM_PLAIN: out[owner * ld + off + column], column < cols
+// GM_PLAIN: out[owner * ld + off + column], column < cols; `set` != nullptr: this format instead of sA[prec], its table
+// starts `row0` rows into the full table
+struct SegPlain { double* out; int64_t ld; int off, cols; const SegSet* set; int64_t row0; };
 int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, const SegPlain* plain, cudaStream_t st);
+int vb_seg_split_rule(const vb_counts* m, int prec);                       // R the row-split cell pass would use (1: none)
+int vb_seg_build_split(vb_counts* m, int prec, cudaStream_t st);           // builds rA[prec] once (R from the rule)
+int vb_seg_launch_cell_split(const vb_counts* m, const EmP& p, int mode, cudaStream_t st);
 int vb_seg_quantise_rows(const vb_counts* m, const EmP& p, cudaStream_t st);   // RP -> RPq before the first SNP pass
 
 // error plumbing -------------------------------------------------------------------------------

@@ -974,6 +974,7 @@ __global__ void __launch_bounds__(VB_THREADS) k_doublet_softmax(const double* __
 static CountsView view_of(const vb_counts* m) {
     CountsView v;
     v.C = m->C; v.V = m->V; v.N = m->N;
+    v.g_lo = 0; v.g_hi = INT64_MAX;
     v.cell_ptr = m->cell_ptr; v.cell_idx = m->cell_idx; v.cell_cnt = m->cell_cnt; v.cell_dp = m->cell_dp;
     v.snp_ptr = m->snp_ptr; v.snp_idx = m->snp_idx; v.snp_cnt = m->snp_cnt; v.snp_dp = m->snp_dp;
     return v;
@@ -1023,6 +1024,7 @@ static bool lane_deep() {
 }
 
 static int launch_cell(const vb_counts* m, const EmP& p, int mode, cudaStream_t st) {
+    if (p.tiled == 2 && !p.bmm && m->rA[p.RW == 8 ? 2 : 0].R > 1) return vb_seg_launch_cell_split(m, p, mode, st);
     if (p.tiled >= 2) return vb_seg_launch(m, p, 0, mode == 0 ? GM_CELL : GM_CELL_LL, 0, nullptr, st);
     int KT, KR;
     if (!tile_for(p.K, KT, KR)) { vb_set_error("n_donor=%d outside [1, %d]", p.K, VB_MAX_DONOR); return VB_E_UNSUPPORTED; }
@@ -1117,6 +1119,7 @@ static int select_family(const vb_counts* mc, int K, int fixed_ok, cudaStream_t 
             if ((rc = vb_seg_build(m, prec, st))) return rc;
         }
         *use = prec == 1 ? 3 : 2;
+        if (*use == 2 && vb_seg_split_rule(m, prec) > 1) vb_seg_build_split(m, prec, st);    // optional: failure keeps the plain cell pass
         return VB_OK;
     }
     // automatic: the window-segment kernels with FP64 tables for large count matrices; row kernels when the passes
@@ -1134,6 +1137,7 @@ static int select_family(const vb_counts* mc, int K, int fixed_ok, cudaStream_t 
     if (m->sA[fp64_fmt].n_heavy * 4 > pairs) { m->auto_fallback = 3; return VB_OK; }
     m->auto_fallback = 0;
     *use = 2;
+    if (vb_seg_split_rule(m, fp64_fmt) > 1) vb_seg_build_split(m, fp64_fmt, st);             // optional, see above
     return VB_OK;
 }
 
@@ -1159,6 +1163,7 @@ static void part_layout(const vb_counts* m, EmP& p) {
     p.n_snpblk = p.tiled >= 2 ? sb : m->grid_snp;
     p.n_elemblk = m->grid_elem;
     p.n_cellblk = p.tiled >= 2 ? sa : m->grid_cell;
+    if (p.tiled == 2 && !p.bmm && m->rA[p.RW == 8 ? 2 : 0].R > 1) p.n_cellblk = m->sm_count;      // row-split cell pass: k_cell_finish
     p.n_klth = (p.bmm || p.ase) ? m->grid_elem : 1;
     p.off_theta = 0;
     p.off_klgt = p.off_theta + cap_snp * 2 * VB_MAX_GT;
@@ -1185,6 +1190,10 @@ static void ws_for(const vb_counts* m, int K, int G, int B, int T_is_V, int use,
         out->rpad += (int64_t)B * m->C * (VB_ROW_DOUBLES / 2);
     }
     out->heavy = use ? (int64_t)B * (m->C > 2 * m->V ? m->C : 2 * m->V) * p.RW : 0;
+    if (use == 2 && !p.bmm) {   // the row-split cell pass keeps its partial sums here: R blocks of [B, C, RW]
+        const int64_t split = (int64_t)vb_seg_split_rule(m, p.RW == 8 ? 2 : 0) * B * m->C * p.RW;
+        if (split > out->heavy) out->heavy = split;
+    }
     out->loglik = (int64_t)B * m->C * K;
     out->ab = (int64_t)B * T * 2 * (G ? G : 1) + (use == 3 ? B : 0);
     out->part = (int64_t)B * p.part_stride;
@@ -1619,7 +1628,7 @@ extern "C" int vb_vireo_doublet(const vb_counts* m, int n_donor, int n_gt, int a
         for (int k0 = 0, c = 0; k0 < K2; k0 += cw, ++c) {
             p.Wt = W + (size_t)c * 2 * m->V * cw;
             SegPlain pl;
-            pl.out = loglik_out; pl.ld = K2; pl.off = k0; pl.cols = K2 - k0 < cw ? K2 - k0 : cw;
+            pl.out = loglik_out; pl.ld = K2; pl.off = k0; pl.cols = K2 - k0 < cw ? K2 - k0 : cw; pl.set = nullptr; pl.row0 = 0;
             const int rc = vb_seg_launch(m, p, 0, GM_PLAIN, 0, &pl, st);
             if (rc) return rc;
         }

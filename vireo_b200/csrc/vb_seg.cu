@@ -266,9 +266,10 @@ static void seg_set_free(SegSet& g) {
     memset(&g, 0, sizeof(g));
 }
 
-static CountsView sg_view(const vb_counts* m) {
+static CountsView sg_view(const vb_counts* m, int64_t g_lo, int64_t g_hi) {
     CountsView v;
     v.C = m->C; v.V = m->V; v.N = m->N;
+    v.g_lo = g_lo; v.g_hi = g_hi;
     v.cell_ptr = m->cell_ptr; v.cell_idx = m->cell_idx; v.cell_cnt = m->cell_cnt; v.cell_dp = m->cell_dp;
     v.snp_ptr = m->snp_ptr; v.snp_idx = m->snp_idx; v.snp_cnt = m->snp_cnt; v.snp_dp = m->snp_dp;
     return v;
@@ -298,12 +299,15 @@ static void seg_window(int prec, int* win_rows, int* nb, int* span) {
     if (*span < 1) *span = 1;
 }
 
+// g_lo / g_hi: the table rows this format covers (all of them: 0 / -1); max_grid: CTAs the launch may use (0: every SM)
 template <int ORI>
-static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
+static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st, int64_t g_lo = 0, int64_t g_hi = -1, int max_grid = 0) {
     memset(&g, 0, sizeof(g));
-    const int sm = m->sm_count;
+    const int sm = max_grid > 0 ? max_grid : m->sm_count;
     const int64_t O = ORI == 0 ? m->C : 2 * m->V;
-    const int64_t Gn = ORI == 0 ? 2 * m->V : m->C;
+    const int64_t G_all = ORI == 0 ? 2 * m->V : m->C;
+    if (g_hi < 0 || g_hi > G_all) g_hi = G_all;
+    const int64_t Gn = g_hi - g_lo;
     if (O >= (1ll << 31) - 64 || Gn >= (1ll << 31) - 4096) { vb_set_error("segment format: more than 2^31 rows"); return VB_E_UNSUPPORTED; }
     int win_rows, nb, span;
     seg_window(prec, &win_rows, &nb, &span);
@@ -312,7 +316,7 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
     int n_win = (int)((Gn + win_rows - 1) / win_rows);
     if (n_win < 1) n_win = 1;
     const int64_t n_task = (O + VB_SEG_OWNERS - 1) / VB_SEG_OWNERS;
-    const CountsView v = sg_view(m);
+    const CountsView v = sg_view(m, g_lo, g_hi);
     GsScratch tmp;
     int rc;
     uint32_t *nl, *nh, *rd, *nl_sorted;
@@ -352,7 +356,7 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
         double total = 0.0;
         for (int64_t r = 0; r < O; ++r) total += hlen[r];
         int64_t first_sparse = O, moved = 0;
-        const int64_t budget = (int64_t)(total / 50.0);
+        const int64_t budget = max_grid > 0 ? 0 : (int64_t)(total / 50.0);      // formats of the row-split pass keep every owner in the stream
         while (first_sparse > 0 && hlen[first_sparse - 1] <= VB_SPARSE_LEN && moved + hlen[first_sparse - 1] <= budget) {
             moved += hlen[first_sparse - 1];
             --first_sparse;
@@ -472,8 +476,10 @@ int vb_seg_build(vb_counts* m, int prec, cudaStream_t st) {
     return rc;
 }
 
+static void seg_split_free(SegSplit& sp);
+
 void vb_seg_free(vb_counts* m) {
-    for (int i = 0; i < 3; ++i) { seg_set_free(m->sA[i]); seg_set_free(m->sB[i]); }
+    for (int i = 0; i < 3; ++i) { seg_set_free(m->sA[i]); seg_set_free(m->sB[i]); seg_split_free(m->rA[i]); }
 }
 
 void vb_seg_geometry(const SegSet& g, int* grid, int* nwarps) {
@@ -624,6 +630,7 @@ __global__ void __launch_bounds__(VB_THREADS) k_seg_quant_rows(const double* __r
 // k_seg
 // ---------------------------------------------------------------------------------------------
 #define VB_SG_RED_DOUBLES (2 * VB_MAX_GT)
+#define VB_SEG_FEW_WARPS 11         // consumer warps per CTA up to which the 4-landing-set instance of k_seg is launched
 // how the producer / the consumers wait for a window barrier (build.py variants "sleepp", "sleeppc")
 #ifdef VB_SEG_SLEEP_P
 #define VB_SEG_PWAIT(bar, par) mbar_wait_sleep(bar, par, VB_SEG_SLEEP_P)
@@ -651,6 +658,7 @@ struct SegArgs {
     double* plain_out;
     int64_t plain_ld;
     int plain_off, plain_cols;
+    int64_t plain_stride;    // doubles between the outputs of consecutive restarts (0: one restart)
 };
 
 template <int PREC> struct SegCfg;
@@ -677,9 +685,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 #define VB_SEG_SETP4 "setp.ne.u32 p, %4, 0;\n\t"
 #define VB_SEG_SETP2 "setp.ne.u32 p, %2, 0;\n\t"
 #endif
-struct SegScratch64 { double v[2][4]; };     // landing registers of the FP64 loads, two sets in flight
+template <int NSET> struct SegScratch64 { double v[NSET][4]; };     // landing registers of the FP64 loads, NSET slots in flight
 struct SegScratch32 {};
-struct SegScratchN { double v[2][2]; };      // narrow FP64 rows: one 16-byte load per lane and record
+template <int NSET> struct SegScratchN { double v[NSET][2]; };      // narrow FP64 rows: one 16-byte load per lane and record
 
 __device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, double (&a)[4], double (&v)[4]) {
     const uint32_t xh = w << 16;
@@ -728,16 +736,17 @@ __device__ __forceinline__ void seg_step(uint32_t w, uint32_t base, unsigned lon
     }
 }
 
-// the two halves of a super-step: slots 0, 1 and slots 2, 3 of the lane group
-template <int H>
-__device__ __forceinline__ void seg_half_step(uint32_t w0, uint32_t w1, uint32_t base, double (&acc)[4][4], SegScratch64& sc) {
-    seg_step(w0, base, acc[2 * H], sc.v[0]); seg_step(w1, base, acc[2 * H + 1], sc.v[1]);
+// the two halves of a super-step: slots 0, 1 and slots 2, 3 of the lane group; with 4 landing sets every slot of a
+// super-step has its own, so the loads of the second half do not wait for the FMAs of the first
+template <int H, int NSET>
+__device__ __forceinline__ void seg_half_step(uint32_t w0, uint32_t w1, uint32_t base, double (&acc)[4][4], SegScratch64<NSET>& sc) {
+    seg_step(w0, base, acc[2 * H], sc.v[(2 * H) % NSET]); seg_step(w1, base, acc[2 * H + 1], sc.v[(2 * H + 1) % NSET]);
 }
-template <int H>
-__device__ __forceinline__ void seg_half_step(uint32_t w0, uint32_t w1, uint32_t base, double (&acc)[4][2], SegScratchN& sc) {
-    seg_step(w0, base, acc[2 * H], sc.v[0]); seg_step(w1, base, acc[2 * H + 1], sc.v[1]);
+template <int H, int NSET>
+__device__ __forceinline__ void seg_half_step(uint32_t w0, uint32_t w1, uint32_t base, double (&acc)[4][2], SegScratchN<NSET>& sc) {
+    seg_step(w0, base, acc[2 * H], sc.v[(2 * H) % NSET]); seg_step(w1, base, acc[2 * H + 1], sc.v[(2 * H + 1) % NSET]);
 }
-template <int H>
+template <int H, int NSET>
 __device__ __forceinline__ void seg_half_step(uint32_t w0, uint32_t w1, uint32_t base, unsigned long long (&acc)[4][4], SegScratch32&) {
     seg_step(w0, base, acc[2 * H]); seg_step(w1, base, acc[2 * H + 1]);
 }
@@ -751,9 +760,12 @@ __device__ __forceinline__ void lds64(uint32_t addr, uint32_t& a, uint32_t& b) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
 }
 
-// 23 warps per SM leave 80 registers per lane (registers are handed out in units of 512 per warp: 88 would count as 96)
-template <int PREC>
-__global__ void __launch_bounds__((VB_SEG_MAX_WARPS + 1) * 32, 1)
+// 23 warps per SM leave 80 registers per lane (registers are handed out in units of 512 per warp: 88 would count as 96).
+// NSET = 2: that budget, two landing sets.  NSET = 4: launches with at most VB_SEG_FEW_WARPS consumer warps per CTA
+// (matrices with few owner rows per SM: GT-given fits on mid-sized data, one rank's share of a cell-sharded fit) are
+// bound by the dependent chain of ONE warp, not by registers -- every slot of a super-step gets its own landing set.
+template <int PREC, int NSET>
+__global__ void __launch_bounds__((NSET == 2 ? VB_SEG_MAX_WARPS + 1 : VB_SEG_FEW_WARPS + 2) * 32, 1)     // NSET 4: one warp of margin
 k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     using Cfg = SegCfg<PREC>;
     constexpr int LPO = Cfg::LPO, M = Cfg::LPO, NC = Cfg::NC, ROWB = Cfg::ROWB, CH = VB_SEG_DEPTH;
@@ -868,14 +880,14 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
     } else if (task >= 0) {
         // ---------------- consumer warp: 32 owner slots, LPO lanes per slot
         const int64_t s0 = sv.task_off[task], s1 = sv.task_off[task + 1];
-        typename std::conditional<PREC == 0, SegScratch64, typename std::conditional<PREC == 1, SegScratch32, SegScratchN>::type>::type sc;
+        typename std::conditional<PREC == 0, SegScratch64<NSET>, typename std::conditional<PREC == 1, SegScratch32, SegScratchN<NSET>>::type>::type sc;
         if constexpr (PREC == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sc.v[i >> 2][i & 3] = 0.0;
+            for (int i = 0; i < 4 * NSET; ++i) sc.v[i >> 2][i & 3] = 0.0;
         }
         if constexpr (PREC == 2) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) sc.v[i >> 1][i & 1] = 0.0;
+            for (int i = 0; i < 2 * NSET; ++i) sc.v[i >> 1][i & 1] = 0.0;
         }
         // this lane's granule of ring row 0, minus the constant upper bits of the count code (see seg_step); FP64
         // rows: odd lane groups read the upper half of a row first
@@ -928,9 +940,9 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
                     c.x &= 0x0fffffffu;
                 }
                 // the records of the next super-step are loaded half by half as soon as this one's are decoded
-                seg_half_step<0>(c.x, c.y, base, acc, sc);
+                seg_half_step<0, NSET>(c.x, c.y, base, acc, sc);
                 if (i + 1 < CH) lds64(cb + (i + 1) * (VB_SEG_OWNERS * 4), c.x, c.y);
-                seg_half_step<1>(c.z, c.w, base, acc, sc);
+                seg_half_step<1, NSET>(c.z, c.w, base, acc, sc);
                 if (i + 1 < CH) lds64(cb + (i + 1) * (VB_SEG_OWNERS * 4) + 8, c.z, c.w);
             }
             __syncwarp();                                 // every lane has read the chunk: refill its buffer
@@ -1048,7 +1060,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
             } else if (sa.mode == GM_PLAIN) {
                 // column chunk of a wider table (doublet pass): plain sums, no softmax
                 if (owner >= 0) {
-                    double* __restrict__ O = sa.plain_out + (size_t)owner * sa.plain_ld + sa.plain_off;
+                    double* __restrict__ O = sa.plain_out + (size_t)b * sa.plain_stride + (size_t)owner * sa.plain_ld + sa.plain_off;
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         const int col = col0 + (c < 2 ? c : col2 + c - 2);
@@ -1137,6 +1149,157 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// row-split cell pass: finish kernel.  partial[r][b][cell][RW] holds the sums of table-row range r (written by k_seg
+// in GM_PLAIN mode); this kernel adds them and does what the cell-mode epilogue of k_seg does: softmax over the donors
+// with the ID prior, ID_prob, logLik_ID, the padded-row copy for the SNP pass, the LB_p / KL_ID block partials
+// (vireoSNP/utils/vireo_model.py:198-201,236-237), then the fused tail.  mode 1: logLik + partials from the present ID_prob.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VB_THREADS)
+k_cell_finish(const EmP p, const double* __restrict__ partial, int R, int mode) {
+    const int b = blockIdx.y;
+    if (p.ctrl && p.ctrl[b * VB_CTRL_N]) return;
+    __shared__ double sh[2 * VB_WARPS];
+    const int K = p.K, KT = p.KT, RW = p.RW;
+    const size_t range_stride = (size_t)p.B * p.C * RW;
+    double r0 = 0.0, r1 = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < p.C; j += (int64_t)gridDim.x * blockDim.x) {
+        const double* __restrict__ src = partial + ((size_t)b * p.C + j) * RW;
+        double v[VB_ROW_DOUBLES];
+#pragma unroll
+        for (int k = 0; k < VB_ROW_DOUBLES; ++k) v[k] = 0.0;
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < VB_ROW_DOUBLES; ++k)
+                if (k < K) v[k] += src[(size_t)r * range_stride + k];
+        const size_t prow = (size_t)(p.id_rows == 1 ? 0 : j) * K;
+        double* __restrict__ Rj = p.R + ((size_t)b * p.C + j) * K;
+        double* __restrict__ LL = p.ll + ((size_t)b * p.C + j) * K;
+        double pr[VB_ROW_DOUBLES];
+        if (mode == 0) {
+            double mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < VB_ROW_DOUBLES; ++k) { pr[k] = k < K ? v[k] + p.lidp[prow + k] : -INFINITY; mx = fmax(mx, pr[k]); }
+            double z = 0.0;
+#pragma unroll
+            for (int k = 0; k < VB_ROW_DOUBLES; ++k) { pr[k] = pr[k] == -INFINITY ? 0.0 : exp(pr[k] - mx); z += pr[k]; }
+#pragma unroll
+            for (int k = 0; k < VB_ROW_DOUBLES; ++k) pr[k] = pr[k] / z;
+            double* __restrict__ RP = p.RP + ((size_t)b * p.C + j) * RW;
+#pragma unroll
+            for (int c = 0; c < VB_ROW_DOUBLES; ++c)
+                if (c < RW) RP[c] = (c % KT) < K ? pr[c % KT] : 0.0;
+        } else {
+#pragma unroll
+            for (int k = 0; k < VB_ROW_DOUBLES; ++k) pr[k] = k < K ? Rj[k] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < VB_ROW_DOUBLES; ++k) {
+            if (k < K) {
+                LL[k] = v[k];
+                if (mode == 0) Rj[k] = pr[k];
+                r0 += v[k] * pr[k];
+                if (pr[k] > 0.0) r1 += pr[k] * (log(pr[k]) - p.lidp_kl[prow + k]);
+            }
+        }
+    }
+    r0 = warp_sum(r0);
+    r1 = warp_sum(r1);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sh[2 * w] = r0; sh[2 * w + 1] = r1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int i = 0; i < VB_WARPS; ++i) { a += sh[2 * i]; c += sh[2 * i + 1]; }
+        double* out = p.part + (size_t)b * p.part_stride + p.off_cell + 2 * blockIdx.x;
+        out[0] = a;
+        out[1] = c;
+    }
+    if (mode == 0) cell_pass_tail(p, b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: row-split cell pass
+// ---------------------------------------------------------------------------------------------
+// R = how many launches side by side fill the SMs with 22-warp CTAs, provided every range keeps enough windows (the
+// partial sums live in the caller's `heavy` workspace, which ws_for sizes for them).  VIREO_B200_SEG_SPLIT=0 turns it off.
+// Measured on one rank's share of cfg3 (scripts/time_shard.py): 4 ranks 0.546 -> 0.468 ms per iteration, 8 ranks 0.471 -> 0.363.
+int vb_seg_split_rule(const vb_counts* m, int prec) {
+    static const int on = env_int("VIREO_B200_SEG_SPLIT", 1);
+    if (!on || prec == 1 || m->C < 1) return 1;
+    int win_rows, nb, span;
+    seg_window(prec, &win_rows, &nb, &span);
+    const int64_t tasks = (m->C + VB_SEG_OWNERS - 1) / VB_SEG_OWNERS;
+    const int64_t n_win = (2 * m->V + win_rows - 1) / win_rows;
+    int64_t R = (int64_t)m->sm_count * VB_SEG_MAX_WARPS / (tasks > 0 ? tasks : 1);
+    if (R > VB_SEG_MAX_SPLIT) R = VB_SEG_MAX_SPLIT;
+    while (R > 1 && n_win / R < 4 * span) --R;
+    return R < 3 ? 1 : (int)R;      // two launches do not pay for the fork / join and the finish kernel (measured at cfg4 and on half of cfg3)
+}
+
+static void seg_split_free(SegSplit& sp) {
+    for (int r = 0; r < VB_SEG_MAX_SPLIT; ++r) {
+        seg_set_free(sp.set[r]);
+        if (sp.aux[r]) cudaStreamDestroy(sp.aux[r]);
+        if (sp.join[r]) cudaEventDestroy(sp.join[r]);
+    }
+    if (sp.fork) cudaEventDestroy(sp.fork);
+    memset(&sp, 0, sizeof(sp));
+}
+
+int vb_seg_build_split(vb_counts* m, int prec, cudaStream_t st) {
+    SegSplit& sp = m->rA[prec];
+    if (sp.R > 0) return VB_OK;
+    if (sp.failed) return VB_E_UNSUPPORTED;
+    const int R = vb_seg_split_rule(m, prec);
+    if (R < 2) { sp.failed = 1; return VB_E_UNSUPPORTED; }
+    DeviceGuard dg(m->device);
+    int win_rows, nb, span;
+    seg_window(prec, &win_rows, &nb, &span);
+    const int64_t n_win = (2 * m->V + win_rows - 1) / win_rows;
+    const int64_t wpr = (n_win + R - 1) / R;
+    int rc = VB_OK;
+    for (int r = 0; r <= R; ++r) sp.row_lo[r] = std::min<int64_t>((int64_t)r * wpr * win_rows, 2 * m->V);
+    for (int r = 0; r < R && !rc; ++r) {
+        rc = seg_build_one<0>(m, sp.set[r], prec, st, sp.row_lo[r], sp.row_lo[r + 1], m->sm_count / R);
+        if (!rc && sp.set[r].n_heavy > 0) { vb_set_error("row-split cell pass: residual pairs"); rc = VB_E_UNSUPPORTED; }   // the partial sums use the residual workspace
+    }
+    for (int r = 0; r < R && !rc; ++r) {
+        if (cudaStreamCreateWithFlags(&sp.aux[r], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sp.join[r], cudaEventDisableTiming) != cudaSuccess) rc = VB_E_CUDA;
+    }
+    if (!rc && cudaEventCreateWithFlags(&sp.fork, cudaEventDisableTiming) != cudaSuccess) rc = VB_E_CUDA;
+    if (rc) {
+        seg_split_free(sp);
+        sp.failed = 1;
+        cudaGetLastError();
+        return rc;
+    }
+    sp.R = R;
+    return VB_OK;
+}
+
+int vb_seg_launch_cell_split(const vb_counts* m, const EmP& p, int mode, cudaStream_t st) {
+    const int prec = p.RW == 8 ? 2 : 0;
+    const SegSplit& sp = m->rA[prec];
+    if (sp.R < 2 || p.tiled != 2) { vb_set_error("row-split cell pass was not built"); return VB_E_ARG; }
+    const size_t range_stride = (size_t)p.B * p.C * p.RW;
+    VB_CUDA(cudaEventRecord(sp.fork, st));
+    for (int r = 0; r < sp.R; ++r) {
+        VB_CUDA(cudaStreamWaitEvent(sp.aux[r], sp.fork, 0));
+        SegPlain pl;
+        pl.out = p.H + (size_t)r * range_stride; pl.ld = p.RW; pl.off = 0; pl.cols = p.RW;
+        pl.set = &sp.set[r]; pl.row0 = sp.row_lo[r];
+        const int rc = vb_seg_launch(m, p, 0, GM_PLAIN, 0, &pl, sp.aux[r]);
+        if (rc) return rc;
+        VB_CUDA(cudaEventRecord(sp.join[r], sp.aux[r]));
+    }
+    for (int r = 0; r < sp.R; ++r) VB_CUDA(cudaStreamWaitEvent(st, sp.join[r], 0));
+    VB_LAUNCH(3, st, k_cell_finish<<<dim3((unsigned)p.n_cellblk, p.B), VB_THREADS, 0, st>>>(p, p.H, sp.R, mode));
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host: dispatch
 // ---------------------------------------------------------------------------------------------
 static SegView view_of_set(const SegSet& g) {
@@ -1154,6 +1317,12 @@ static size_t seg_smem(int prec, int nb, int win_rows) {
     return VB_SG_RING_OFF + (size_t)nb * win_rows * (prec == 0 ? 128 : 64) + (size_t)VB_SEG_MAX_WARPS * 2 * VB_SEG_DEPTH * VB_SEG_OWNERS * 4;
 }
 
+// VIREO_B200_SEG_FEW=0 keeps the two-landing-set instance for every launch
+static bool seg_few_on() {
+    static const bool on = !(getenv("VIREO_B200_SEG_FEW") && atoi(getenv("VIREO_B200_SEG_FEW")) == 0);
+    return on;
+}
+
 static bool g_seg_attr_set[64] = {false};     // per device: function attributes belong to the context
 static size_t g_seg_static[64] = {0};         // largest static shared memory of the k_seg instances
 #define VB_SMEM_OPTIN ((size_t)227 * 1024)
@@ -1162,7 +1331,7 @@ static size_t g_seg_static[64] = {0};         // largest static shared memory of
 // mode GM_PLAIN (ori 0, FP64 tables): `plain` says where the sums of this column chunk go
 int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, const SegPlain* plain, cudaStream_t st) {
     const int prec = p.tiled == 3 ? 1 : (p.RW == 8 ? 2 : 0);
-    const SegSet& g = ori ? m->sB[prec] : m->sA[prec];
+    const SegSet& g = (plain && plain->set) ? *plain->set : (ori ? m->sB[prec] : m->sA[prec]);
     if (!g.built) { vb_set_error("segment format was not built"); return VB_E_ARG; }
     const int dev_slot = m->device >= 0 && m->device < 64 ? m->device : 0;
     if (!g_seg_attr_set[dev_slot]) {
@@ -1180,7 +1349,8 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
             }
             if (fa.sharedSizeBytes > st_max) st_max = fa.sharedSizeBytes;
         };
-        opt_in((const void*)k_seg<0>); opt_in((const void*)k_seg<1>); opt_in((const void*)k_seg<2>);
+        opt_in((const void*)k_seg<0, 2>); opt_in((const void*)k_seg<1, 2>); opt_in((const void*)k_seg<2, 2>);
+        opt_in((const void*)k_seg<0, 4>); opt_in((const void*)k_seg<2, 4>);
         if (rc_attr) return rc_attr;
         g_seg_static[dev_slot] = st_max;
         g_seg_attr_set[dev_slot] = true;
@@ -1193,12 +1363,17 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
     memset(&sa, 0, sizeof(sa));
     sa.mode = mode; sa.theta_mode = theta_mode;
     const double* tab64 = ori ? p.RP : p.Wt;
-    if (prec != 1) { sa.table = reinterpret_cast<const unsigned char*>(tab64); sa.table_stride = g.n_gather * (prec == 0 ? 128 : 64); }
-    else { sa.table = reinterpret_cast<const unsigned char*>(ori ? p.RPq : p.Wq); sa.table_stride = g.n_gather * 64; }
+    const int64_t rows_all = ori ? p.C : 2 * p.V;                  // the table of one restart, whatever part of it `g` covers
+    if (prec != 1) {
+        sa.table = reinterpret_cast<const unsigned char*>(tab64) + (size_t)((plain && plain->set) ? plain->row0 : 0) * (prec == 0 ? 128 : 64);
+        sa.table_stride = rows_all * (prec == 0 ? 128 : 64);
+    }
+    else { sa.table = reinterpret_cast<const unsigned char*>(ori ? p.RPq : p.Wq); sa.table_stride = rows_all * 64; }
     sa.has_heavy = g.n_heavy > 0;
     if (mode == GM_PLAIN) {
         if (!plain || prec == 1 || ori != 0) { vb_set_error("plain segment pass: bad arguments"); return VB_E_ARG; }
         sa.plain_out = plain->out; sa.plain_ld = plain->ld; sa.plain_off = plain->off; sa.plain_cols = plain->cols;
+        sa.plain_stride = plain->set ? (int64_t)p.C * plain->ld : 0;      // row-split cell pass: one block of sums per restart
     }
     int grid_x;
     vb_seg_geometry(g, &grid_x, &sa.nwarps);
@@ -1214,9 +1389,10 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
     const dim3 grid(grid_x, p.B);
     const int threads = (sa.nwarps + 1) * 32;
     VB_LAUNCH(cls, st, {
-        if (prec == 2) k_seg<2><<<grid, threads, smem, st>>>(sv, p, sa);
-        else if (prec == 0) k_seg<0><<<grid, threads, smem, st>>>(sv, p, sa);
-        else k_seg<1><<<grid, threads, smem, st>>>(sv, p, sa);
+        const bool few = sa.nwarps <= VB_SEG_FEW_WARPS && seg_few_on();
+        if (prec == 2) { if (few) k_seg<2, 4><<<grid, threads, smem, st>>>(sv, p, sa); else k_seg<2, 2><<<grid, threads, smem, st>>>(sv, p, sa); }
+        else if (prec == 0) { if (few) k_seg<0, 4><<<grid, threads, smem, st>>>(sv, p, sa); else k_seg<0, 2><<<grid, threads, smem, st>>>(sv, p, sa); }
+        else k_seg<1, 2><<<grid, threads, smem, st>>>(sv, p, sa);
     });
     VB_CUDA(cudaGetLastError());
     return VB_OK;

@@ -185,6 +185,7 @@ extern "C" int64_t vb_counts_info(const vb_counts* m, int what) {
         case 7: return m->grid_snp;
         case 8: return m->grid_elem;
         case 60: return m->auto_fallback;
+        case 61: return m->rA[0].R > m->rA[2].R ? m->rA[0].R : m->rA[2].R;      // launches of the row-split cell pass (0: not in use)
         // window-segment formats: 20 + 10 * precision + {0 built, 1 / 2 super-steps of the cell / SNP pass,
         // 3 / 4 largest reads of one owner's stream (cell / SNP pass), 5 / 6 grid.x, 7 bytes, 8 residual pairs, 9 stream pairs}
         default: break;

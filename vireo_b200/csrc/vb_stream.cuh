@@ -15,20 +15,21 @@ __device__ __forceinline__ void counts_at(const uint32_t* __restrict__ cnt, cons
 }
 
 // ORI 0: owner = cell j, gather row = 2*snp + allele;  ORI 1: owner = 2*snp + allele, gather row = cell.
-// Calls f(gather_row, count) for every pair with count > 0 in ascending gather-row order; returns false
-// if a count pair with ad > dp was met (the formats do not represent it).
+// Calls f(gather_row - m.g_lo, count) for every pair with count > 0 and a gather row in [m.g_lo, m.g_hi), in ascending
+// gather-row order; returns false if a count pair with ad > dp was met (the formats do not represent it).
 template <int ORI, bool WIDE, typename F>
 __device__ __forceinline__ bool for_records(const CountsView& m, int64_t o, F&& f) {
     bool ok = true;
+    const int64_t lo = m.g_lo, hi = m.g_hi;
     if (ORI == 0) {
         const int64_t p0 = m.cell_ptr[o], p1 = m.cell_ptr[o + 1];
         for (int64_t q = p0; q < p1; ++q) {
             uint32_t a, d;
             counts_at<WIDE>(m.cell_cnt, m.cell_dp, q, a, d);
             if (a > d) { ok = false; continue; }
-            const int i = m.cell_idx[q];
-            if (d - a) f(2 * i, d - a);
-            if (a) f(2 * i + 1, a);
+            const int64_t g = 2 * (int64_t)m.cell_idx[q];
+            if (d - a && g >= lo && g < hi) f((int)(g - lo), d - a);
+            if (a && g + 1 >= lo && g + 1 < hi) f((int)(g + 1 - lo), a);
         }
     } else {
         const int64_t i = o >> 1;
@@ -39,7 +40,8 @@ __device__ __forceinline__ bool for_records(const CountsView& m, int64_t o, F&& 
             counts_at<WIDE>(m.snp_cnt, m.snp_dp, q, a, d);
             if (a > d) { ok = false; continue; }
             const uint32_t c = al ? a : d - a;
-            if (c) f(m.snp_idx[q], c);
+            const int64_t g = m.snp_idx[q];
+            if (c && g >= lo && g < hi) f((int)(g - lo), c);
         }
     }
     return ok;
