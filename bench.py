@@ -707,7 +707,7 @@ def run_b200(args):
 def measure_sharded_fit(torch, dist, vb, rank, world, barrier, counts, w, init, iters=100):
     """One fit of `iters` fixed iterations through the public API (host state in, host results out): cells sharded over
     all ranks (vb.fit_cell_sharded) vs the same fit on one GPU (rank 0 alone).  Both legs exclude the one-off cut of
-    the cell shard (timed separately)."""
+    the cell shard (timed separately) and the construction of the model object."""
     C_, V, K = w["C"], w["V"], w["K"]
     from vireo_b200.sharded import shard_of
 
@@ -725,10 +725,10 @@ def measure_sharded_fit(torch, dist, vb, rank, world, barrier, counts, w, init, 
     vb.fit_cell_sharded(fresh(), counts, None, max_iter=3, min_iter=3, verbose=False)     # first use: formats, NCCL
     import importlib
     sh = importlib.import_module("vireo_b200.sharded")
+    ms_ = fresh()                                # the model object (host-side normalisation of the initial state) is not the fit
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    ms_ = fresh()
     vb.fit_cell_sharded(ms_, counts, None, **kw)
     torch.cuda.synchronize()
     t_sh = _max_over_ranks(torch, dist, world, time.perf_counter() - t0)
@@ -743,9 +743,9 @@ def measure_sharded_fit(torch, dist, vb, rank, world, barrier, counts, w, init, 
     out = None
     if rank == 0:
         fresh().fit(counts, None, max_iter=3, min_iter=3, verbose=False)
+        m1 = fresh()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        m1 = fresh()
         m1.fit(counts, None, **kw)
         torch.cuda.synchronize()
         t_one = time.perf_counter() - t0
