@@ -284,7 +284,7 @@ def workload_config(args, w, nnz):
         "n_init": args.gpus * args.restarts,
         "restarts_per_gpu": args.restarts,
         "parallelism": "restart-sharded x%d, full matrices on every GPU" % args.gpus,
-        "l2": "inputs larger than L2: every pass streams its whole record stream from HBM (measured 0.35 GB per pass "
+        "l2": "inputs larger than L2: every pass streams its whole record stream from HBM (measured 0.52 GB per pass "
               "at cfg3, 126 MB L2; %.2f GB in the 8 B/nnz row format) -- no flush needed" % (nnz * 8 / 1e9),
     }
 
