@@ -357,6 +357,18 @@ def test_row_split_cell_pass_vs_oracle(vb):
         rel_close(m.ID_prob, o.ID_prob, P_TOL, "ID_prob (GT given)")
         assert np.array_equal(m.ID_prob.argmax(1), o.ID_prob.argmax(1))
         assert (m.ID_prob.argmax(1) == donor).mean() > 0.99
+
+        # restarts batched in grid.y go through the same split (one block of partial sums per restart): a batch of three
+        # equals the three fits done one by one, bit for bit
+        from vireo_b200 import _engine
+        def trio():
+            np.random.seed(7)
+            return [vb.Vireo(n_cell=C, n_var=V, n_donor=K) for _ in range(3)]
+        together, alone = trio(), trio()
+        tr_b = _engine.vireo_fit_models(counts, together, 6, 6, 1e-2, 2, False)
+        tr_a = [_engine.vireo_fit_models(counts, [m1], 6, 6, 1e-2, 2, False)[0] for m1 in alone]
+        for mb, ma, eb, ea in zip(together, alone, tr_b, tr_a):
+            assert np.array_equal(eb, ea) and np.array_equal(mb.ID_prob, ma.ID_prob) and np.array_equal(mb.GT_prob, ma.GT_prob)
     finally:
         _lib.set_path("auto")
         vb.clear_cache()
