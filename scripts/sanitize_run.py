@@ -56,13 +56,14 @@ for path in paths:
     m4.fit(AD4, DP4, max_iter=3, min_iter=3, verbose=False)
     b = vb.BinomMixtureVB(n_cell=C, n_var=V // 2, n_donor=4)
     b.fit(AD4, DP4, n_init=3, max_iter=4, max_iter_pre=3, min_iter=2, random_seed=1, verbose=False)
-    np.random.seed(3)
-    ms = vb.Vireo(n_cell=200, n_var=12500, n_donor=16)
-    ms.fit(ADs, DPs, max_iter=3, min_iter=3, delay_fit_theta=1, verbose=False)
-    print("%-5s split launches %d digest %s" % (path, int(_lib.load().vb_counts_info(vb.stage(ADs, DPs).handle, 61)),
-                                                 digest(ms.ELBO_, ms.ID_prob, ms.GT_prob)))
     print("%-5s ELBO %.10f  digest fit %s doublet %s sharded %s k4 %s bmm %s" % (
         path, m.ELBO_[-1], digest(m.ELBO_, m.ID_prob, m.GT_prob), digest(dbl, sgl, llr),
         digest(s.ELBO_, s.ID_prob), digest(m4.ELBO_, m4.ID_prob), digest(b.ELBO_iters, b.ID_prob)))
+    if os.environ.get("VIREO_B200_SAN_NOSPLIT") != "1":      # the long-table case (window buffers are refilled)
+        np.random.seed(3)
+        ms = vb.Vireo(n_cell=200, n_var=12500, n_donor=16)
+        ms.fit(ADs, DPs, max_iter=3, min_iter=3, delay_fit_theta=1, verbose=False)
+        print("%-5s split launches %d digest %s" % (path, int(_lib.load().vb_counts_info(vb.stage(ADs, DPs).handle, 61)),
+                                                     digest(ms.ELBO_, ms.ID_prob, ms.GT_prob)))
     vb.clear_cache()
 _lib.set_path("auto")
