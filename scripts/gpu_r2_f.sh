@@ -2,7 +2,7 @@
 # round 2: where does the segment kernel's time go -- diagnostic builds (no table loads / no window hand-over), then ncu
 mkdir -p gpurun_out
 L=vireo_b200/libvireo_b200
-for V in "" _nolds _nosync _noldsnosync; do
+for V in "" _nolds; do
   VIREO_B200_LIB=$PWD/${L}${V}.so timeout 300 python scripts/time_passes.py cfg3 10 "variant${V}" 2>/dev/null | tail -1 | tee -a gpurun_out/diag_f.jsonl | cut -c1-330
 done
 bash scripts/gpu_ncu_seg.sh seg cfg3

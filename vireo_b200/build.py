@@ -27,12 +27,10 @@ def nvcc_path():
 
 # sanitizer variants: same sources, one macro (see vb_seg.cu); built on demand, loaded through VIREO_B200_LIB
 VARIANTS = {"plainfill": ["-DVB_SEG_PLAIN_FILL", "-DVB_SEG_CANARY"], "canary": ["-DVB_SEG_CANARY"],
-            # timing diagnostics of the segment kernels (results are garbage by design): no table loads / no window
-            # synchronisation in the consumer warps / both
-            "nolds": ["-DVB_SEG_DIAG_NOLDS"], "nosync": ["-DVB_SEG_DIAG_NOSYNC"],
-            "noldsnosync": ["-DVB_SEG_DIAG_NOLDS", "-DVB_SEG_DIAG_NOSYNC"],
-            # window waits with the warp asleep between polls: producer only / producer and consumers
-            "sleepp": ["-DVB_SEG_SLEEP_P=256"], "sleeppc": ["-DVB_SEG_SLEEP_P=256", "-DVB_SEG_SLEEP_C=64"]}
+            # timing diagnostic of the segment kernels (results are garbage by design): the table loads never execute
+            "nolds": ["-DVB_SEG_DIAG_NOLDS"],
+            # window waits that spin on try_wait instead of sleeping between polls
+            "spin": ["-DVB_SEG_SLEEP_P=0", "-DVB_SEG_SLEEP_C=0"]}
 
 
 def up_to_date(lib=LIB):

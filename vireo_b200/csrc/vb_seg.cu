@@ -631,13 +631,21 @@ __global__ void __launch_bounds__(VB_THREADS) k_seg_quant_rows(const double* __r
 // ---------------------------------------------------------------------------------------------
 #define VB_SG_RED_DOUBLES (2 * VB_MAX_GT)
 #define VB_SEG_FEW_WARPS 11         // consumer warps per CTA up to which the 4-landing-set instance of k_seg is launched
-// how the producer / the consumers wait for a window barrier (build.py variants "sleepp", "sleeppc")
-#ifdef VB_SEG_SLEEP_P
+// How the producer / the consumers wait for a window barrier: a warp that spins on try_wait competes with the working
+// warps of its scheduler for every issue cycle, so between polls it sleeps (nanoseconds; 0 = spin).  Measured at cfg3:
+// 773 -> 782 it/s with 256 / 64; 512 / 128 and 128 / 32 give less, 1024 / 256 loses (build.py variant "spin" = 0 / 0).
+#ifndef VB_SEG_SLEEP_P
+#define VB_SEG_SLEEP_P 256
+#endif
+#ifndef VB_SEG_SLEEP_C
+#define VB_SEG_SLEEP_C 64
+#endif
+#if VB_SEG_SLEEP_P > 0
 #define VB_SEG_PWAIT(bar, par) mbar_wait_sleep(bar, par, VB_SEG_SLEEP_P)
 #else
 #define VB_SEG_PWAIT(bar, par) mbar_wait(bar, par)
 #endif
-#ifdef VB_SEG_SLEEP_C
+#if VB_SEG_SLEEP_C > 0
 #define VB_SEG_CWAIT(bar, par) mbar_wait_sleep(bar, par, VB_SEG_SLEEP_C)
 #else
 #define VB_SEG_CWAIT(bar, par) mbar_wait(bar, par)
@@ -819,9 +827,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
             int bi = 0;
             uint32_t use = 0;                               // how often buffer bi has been filled before
             for (int wd = 0; wd < sv.n_win; ++wd) {
-#ifndef VB_SEG_DIAG_NOSYNC
                 if (use > 0) VB_SEG_PWAIT(bars + 8 * (NB + bi), (use - 1) & 1);   // every consumer released the previous fill
-#endif
 #ifdef VB_SEG_CANARY
                 // Protocol canary (build.py variants "canary" / "plainfill"): a released buffer is overwritten with NaNs
                 // before it is refilled.  A consumer that read a row before its window's fill had completed, or after it
@@ -869,9 +875,7 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
             }
             // a warp that advances near the end of the table waits for windows past it: complete their barriers empty
             for (int wd = 0; wd < sv.span; ++wd) {
-#ifndef VB_SEG_DIAG_NOSYNC
                 if (use > 0) VB_SEG_PWAIT(bars + 8 * (NB + bi), (use - 1) & 1);
-#endif
                 if (lane == 0) mbar_arrive(bars + 8 * bi);
                 __syncwarp();
                 if (++bi == NB) { bi = 0; ++use; }
@@ -896,19 +900,15 @@ k_seg(const SegView sv, const EmP p, const SegArgs sa) {
         const int span = sv.span;
         // The warp holds `span` consecutive windows.  rs: buffer of the oldest one, with the fill parity of that buffer's
         // current window in bit 31.  An advance releases the oldest window and waits for the one behind the newest.
-#ifndef VB_SEG_DIAG_NOSYNC
         for (int wd = 0; wd < span; ++wd) mbar_wait(bars + 8 * wd, 0);
-#endif
         uint32_t rs = 0;
         auto advance = [&]() {
             __syncwarp();                                 // every lane's reads of the oldest window are done
             const uint32_t ri = rs & 0xffffu;
             uint32_t ni = ri + (uint32_t)span, np = rs >> 31;
             if (ni >= (uint32_t)NB) { ni -= (uint32_t)NB; np ^= 1u; }
-#ifndef VB_SEG_DIAG_NOSYNC     // timing diagnostic (build.py variant "nosync"): no window hand-over at all
             if (lane == 0) mbar_arrive(bars + 8 * ((uint32_t)NB + ri));
             VB_SEG_CWAIT(bars + 8 * ni, np);
-#endif
             if ((++rs & 0xffffu) == (uint32_t)NB) rs = (rs & 0x80000000u) ^ 0x80000000u;
         };
         // The record stream of the task arrives in chunks of CH super-steps (512 bytes), bulk-copied into this warp's
