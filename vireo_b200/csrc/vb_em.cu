@@ -414,9 +414,13 @@ __device__ __forceinline__ void load_row(const double* __restrict__ row, int K, 
     }
 }
 
+#ifndef VB_LANE_MINB
+#define VB_LANE_MINB 4          // resident CTAs per SM the shallow lane kernels are compiled for (64 registers; 5 or 6
+                                // -- 48 / 40 registers -- spill and were slower at cfg2 and cfg5)
+#endif
 // U = records per lane and round (more in flight per lane against fewer warps per SM: more registers)
 template <int KP, bool WIDE, int U>
-__global__ void __launch_bounds__(VB_THREADS, U * KP <= 8 ? 4 : 2)
+__global__ void __launch_bounds__(VB_THREADS, U * KP <= 8 ? VB_LANE_MINB : 2)
 k_cell_lane(const CountsView m, const EmP p, const int mode) {
     constexpr int GW = 32 / KP;                            // lanes per column after the fold
     const int b = blockIdx.y;
@@ -500,7 +504,7 @@ k_cell_lane(const CountsView m, const EmP p, const int mode) {
 }
 
 template <int KP, bool WIDE, int U>
-__global__ void __launch_bounds__(VB_THREADS, U * KP <= 8 ? 4 : 2)
+__global__ void __launch_bounds__(VB_THREADS, U * KP <= 8 ? VB_LANE_MINB : 2)
 k_snp_lane(const CountsView m, const EmP p, const int theta_mode) {
     constexpr int GW = 32 / KP;
     const int b = blockIdx.y;
