@@ -47,11 +47,10 @@
 // ----------------------------------------------------------------------------------------------
 #define VB_SEG_OWNERS 32
 #define VB_SEG_MAX_WARPS 22               // consumer warps per CTA (+1 producer warp)
-#define VB_SEG_DEPTH 4                    // a task's stream is padded to a multiple of this many super-steps
+#define VB_SEG_DEPTH 4                    // super-steps per record chunk: a task's stream is padded to a multiple of it
 #define VB_SEG_ADV_MAX 15                 // window advances one super-step can carry
 #define VB_SEG_MAX_RING_ROWS 4096         // 12-bit ring row
 #define VB_SEG_MAX_NB 16
-#define VB_SEG_L2_AHEAD 8192              // bytes of the record stream requested into L2 ahead of the register queue
 
 struct SegSet {
     int built;

@@ -27,6 +27,11 @@
 //   * the count is stored as the upper 16 bits of the double 2 * count: one shift makes the FMA operand, and
 //     because those bits are the same for every count the address is ONE shift-add of the whole record (the
 //     stray bits are a constant folded into the lane base).  The factor 2 leaves in the epilogue (exact);
+//   * the record stream of a task reaches its warp through shared memory as well: two 512-byte chunk buffers per
+//     consumer warp, refilled by the warp's own lane 0 with cp.async.bulk two chunks ahead -- no register queue and
+//     no exposed L2 latency in the loop;
+//   * launches with few warps per CTA use an instance with four landing sets; matrices with few cells but a long
+//     table split the table rows over several launches side by side and add the partial sums in k_cell_finish;
 //   * PREC 0: FP64 tables of 16 columns (rows of 128 bytes);  PREC 2: FP64 tables of 8 columns for
 //     n_donor <= 8 (rows of 64 bytes);  PREC 1 (opt-in) keeps 16 columns as unsigned 32-bit fixed point
 //     (rows of 64 bytes: half the crossbar traffic) and accumulates count * value exactly in 64-bit
@@ -430,8 +435,8 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st, int
         if ((rc = tmp.alloc((unsigned char**)&cub_tmp, tb))) return rc;
         VB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, hw, g.hptr, O + 1, st));
     }
-    // slack: the register queue runs `depth` super-steps ahead, the L2 prefetch VB_SEG_L2_AHEAD bytes
-    const size_t n_rec = ((size_t)total_steps + 2 * depth) * VB_SEG_OWNERS + VB_SEG_L2_AHEAD / 4 + 256;
+    // the kernel reads whole chunks of `depth` super-steps and nothing past the last one; a little slack all the same
+    const size_t n_rec = ((size_t)total_steps + 2 * depth) * VB_SEG_OWNERS + 256;
     VB_CUDA(cudaMalloc(&g.rec, n_rec * sizeof(uint32_t)));
     VB_CUDA(cudaMemsetAsync(g.rec, 0, n_rec * sizeof(uint32_t), st));
     if (n_tw) {
