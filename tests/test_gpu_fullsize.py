@@ -318,6 +318,12 @@ def test_segment_format_holds_every_pair_exactly_once(vb, shape):
             _lib.check(lib.vb_seg_verify(counts.handle, kind, ori, out))
             assert out[0] == n_pairs, (kind, ori, list(out), n_pairs)
             assert out[1] == 0, "format kind %d pass %d: %d errors %s" % (kind, ori, out[1], list(out))
+    # the row-imbalance diagnostic (per mille of longest row / mean row over the built formats)
+    skew = int(lib.vb_counts_info(counts.handle, 62))
+    if shape == "poisson":
+        assert 1000 <= skew < 2500, skew
+    elif shape == "heavy_tail":
+        assert skew > 4000, skew
 
 
 def test_row_split_cell_pass_vs_oracle(vb):

@@ -120,6 +120,7 @@ class StagedCounts:
         self._pool = {}                            # workspaces of finished batches, re-used by the next one
         self._shards = {}                          # (world, rank) -> (StagedCounts of this rank's cells, c0, c1, bounds)
         self._warned = False
+        self._warned_skew = False
         self._finalizer = weakref.finalize(self, lib.vb_counts_destroy, handle)
 
     @classmethod
@@ -167,6 +168,14 @@ class StagedCounts:
             warnings.warn("vireo_b200: the window-segment formats could not be built (%s); falling back to the row "
                           "kernels, which are several times slower on large matrices"
                           % (note.decode() if note else "?"), RuntimeWarning, stacklevel=3)
+        if not self._warned_skew:
+            skew = int(_lib.load().vb_counts_info(self.handle, 62))
+            if skew > 8000:
+                self._warned_skew = True
+                import warnings
+                warnings.warn("vireo_b200: one row of the count matrices carries %.0f times the mean number of entries; "
+                              "the window-segment kernels are as slow as their longest row (DESIGN.md, section 8)"
+                              % (skew / 1000.0), RuntimeWarning, stacklevel=3)
 
     def binom_const(self):
         """float32 sum over nnz of min(log C(dp, ad), 700): the constant ``Vireo.fit`` adds to the ELBO

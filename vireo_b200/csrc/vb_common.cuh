@@ -64,6 +64,7 @@ struct SegSet {
     int64_t n_light;         // pairs carried by the streams
     int64_t n_heavy;         // pairs in the residual
     int64_t max_reads;       // largest sum of counts over one owner's stream pairs (fixed-point error bound)
+    int64_t max_len;         // stream pairs of the longest owner (a task is as long as its longest owner)
     int32_t* perm;           // [n_task*32] owner id of each slot, -1 = padding
     int64_t* task_off;       // [n_task_stream + 1] first super-step of each task (multiples of VB_SEG_DEPTH)
     int32_t* tail;           // [n_task_stream] window advances left when a task's stream ends

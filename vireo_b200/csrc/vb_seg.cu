@@ -380,6 +380,7 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st, int
     }
     g.n_owner = O; g.n_gather = Gn; g.n_task = n_task; g.n_win = n_win; g.win_rows = win_rows; g.nb = nb; g.span = span; g.fixed = fixed;
     g.n_light = (int64_t)hsums[0]; g.n_heavy = (int64_t)hsums[1]; g.max_reads = (int64_t)hsums[2];
+    g.max_len = O ? (int64_t)hlen[0] : 0;
     g.n_task_stream = (n_active + VB_SEG_OWNERS - 1) / VB_SEG_OWNERS;
     const int64_t nts = g.n_task_stream;
 

@@ -186,6 +186,16 @@ extern "C" int64_t vb_counts_info(const vb_counts* m, int what) {
         case 8: return m->grid_elem;
         case 60: return m->auto_fallback;
         case 61: return m->rA[0].R > m->rA[2].R ? m->rA[0].R : m->rA[2].R;      // launches of the row-split cell pass (0: not in use)
+        case 62: {   // worst row imbalance of the built segment formats, per mille: 1000 * longest owner / mean owner
+            int64_t worst = 0;
+            for (int q = 0; q < 3; ++q)
+                for (const SegSet* g : {&m->sA[q], &m->sB[q]})
+                    if (g->built && g->n_light > 0 && g->n_owner > 0) {
+                        const int64_t r = (int64_t)(1000.0 * (double)g->max_len * (double)g->n_owner / (double)g->n_light);
+                        if (r > worst) worst = r;
+                    }
+            return worst;
+        }
         // window-segment formats: 20 + 10 * precision + {0 built, 1 / 2 super-steps of the cell / SNP pass,
         // 3 / 4 largest reads of one owner's stream (cell / SNP pass), 5 / 6 grid.x, 7 bytes, 8 residual pairs, 9 stream pairs}
         default: break;
