@@ -94,7 +94,8 @@ int vb_counts_slice(const vb_counts* m, int64_t cell_begin, int64_t cell_end, vo
  *     pass are cut into that many ranges that run side by side and a finish kernel adds their partial sums;
  * 62: worst row imbalance of the built window-segment formats, per mille (1000 x pairs of the longest row / mean pairs
  *     per row).  A warp task is as long as its longest row, so a row many times heavier than the mean (coverage of real
- *     data is heavy-tailed) becomes the critical path of its pass; the Python layer warns above 8000 */
+ *     data is heavy-tailed) becomes the critical path of its pass; the Python layer warns above 8000.  The builder
+ *     cuts rows above twice the mean into parts when the longest exceeds four times the mean (63 counts the parts) */
 int64_t vb_counts_info(const vb_counts* m, int what);
 /* message of the failed format build behind vb_counts_info(m, 60) == 2 ("" otherwise) */
 const char* vb_counts_note(const vb_counts* m);

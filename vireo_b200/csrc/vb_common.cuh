@@ -52,6 +52,7 @@
 #define VB_SEG_MAX_RING_ROWS 4096         // 12-bit ring row
 #define VB_SEG_MAX_NB 16
 
+struct SegSet;
 struct SegSet {
     int built;
     int64_t n_owner, n_gather;
@@ -68,6 +69,16 @@ struct SegSet {
     int32_t* perm;           // [n_task*32] owner id of each slot, -1 = padding
     int64_t* task_off;       // [n_task_stream + 1] first super-step of each task (multiples of VB_SEG_DEPTH)
     int32_t* tail;           // [n_task_stream] window advances left when a task's stream ends
+    // Rows far heavier than the rest (a task is as long as its longest owner): owner o keeps every o_split[o]-th of its
+    // stream pairs, the others go to o_split[o] - 1 *virtual owners* of the format `excess`, whose plain sums (vsum) are
+    // added to the residual sums H[o] before this format's kernel runs.  nullptr / 0 when no row needed it.
+    uint8_t* o_split;        // [n_owner] parts per owner (1: whole)
+    int64_t n_virtual;       // owners of `excess`
+    int32_t* v_owner;        // [n_virtual] the real owner of a virtual owner (ascending)
+    uint8_t* v_part;         // [n_virtual] which part of it (1 .. o_split - 1)
+    SegSet* excess;
+    double* vsum;            // [B, n_virtual, RW] plain sums of the virtual owners, grown on demand
+    int64_t vsum_elems;
     uint32_t* rec;           // [n_step*32 + slack]
     int64_t* hptr;           // [n_owner+1] residual CSR
     int32_t* hrow;
@@ -150,6 +161,11 @@ void vb_seg_free(vb_counts* m);
 struct CountsView {
     int64_t C, V, N;
     int64_t g_lo, g_hi;        // segment-format builders: only pairs with a gather row in [g_lo, g_hi), rebased to g_lo
+    // segment-format builders, split owners (SegSet::o_split): owner index -> real owner and the part it enumerates
+    int fixed;                 // count code of the format (which counts ride in the stream)
+    const uint8_t* __restrict__ o_split;
+    const int32_t* __restrict__ v_owner;
+    const uint8_t* __restrict__ v_part;
     const int64_t* __restrict__ cell_ptr;
     const int32_t* __restrict__ cell_idx;
     const uint32_t* __restrict__ cell_cnt;

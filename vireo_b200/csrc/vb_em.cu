@@ -979,6 +979,7 @@ static CountsView view_of(const vb_counts* m) {
     CountsView v;
     v.C = m->C; v.V = m->V; v.N = m->N;
     v.g_lo = 0; v.g_hi = INT64_MAX;
+    v.fixed = 0; v.o_split = nullptr; v.v_owner = nullptr; v.v_part = nullptr;
     v.cell_ptr = m->cell_ptr; v.cell_idx = m->cell_idx; v.cell_cnt = m->cell_cnt; v.cell_dp = m->cell_dp;
     v.snp_ptr = m->snp_ptr; v.snp_idx = m->snp_idx; v.snp_cnt = m->snp_cnt; v.snp_dp = m->snp_dp;
     return v;

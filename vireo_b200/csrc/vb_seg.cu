@@ -53,15 +53,6 @@
 // ---------------------------------------------------------------------------------------------
 // count codes
 // ---------------------------------------------------------------------------------------------
-// FP64 tables: a count rides in a record when 2 * count is exact in a double cut to 4 mantissa bits, i.e. when it has
-// at most 5 significant bits (1..31, 32, 34, ..., 62, 64, 68, ...); fixed-point tables: counts up to 31.
-__host__ __device__ inline bool seg_count_ok(uint32_t c, int fixed) {
-    if (fixed) return c <= 31u;
-    if (c >= (1u << 24)) return false;
-    uint32_t t = c;
-    while (t >= 32u) { if (t & 1u) return false; t >>= 1; }
-    return true;
-}
 __host__ __device__ inline uint32_t seg_count_code(uint32_t c, int fixed) {
     if (fixed) return c;
     // 2c = m * 2^e with 16 <= m < 32 (or c < 16: subnormal-free small integers): build the upper half directly
@@ -268,13 +259,27 @@ __global__ void k_sg_fill(const CountsView m, int64_t n_owner, int64_t n_active,
 static void seg_set_free(SegSet& g) {
     cudaFree(g.perm); cudaFree(g.task_off); cudaFree(g.tail); cudaFree(g.rec);
     cudaFree(g.hptr); cudaFree(g.hrow); cudaFree(g.hcnt);
+    cudaFree(g.o_split); cudaFree(g.v_owner); cudaFree(g.v_part); cudaFree(g.vsum);
+    if (g.excess) { seg_set_free(*g.excess); delete g.excess; }
     memset(&g, 0, sizeof(g));
 }
 
-static CountsView sg_view(const vb_counts* m, int64_t g_lo, int64_t g_hi) {
+// what a format covers: the table rows [g_lo, g_hi) (all of them: 0 / -1), on at most max_grid CTAs (0: every SM); split
+// owners: o_split alone = part 0 of every real owner, with v_owner / v_part = the n_virtual virtual owners
+struct SegBuildOpts {
+    int64_t g_lo = 0, g_hi = -1;
+    int max_grid = 0;
+    const uint8_t* o_split = nullptr;
+    const int32_t* v_owner = nullptr;
+    const uint8_t* v_part = nullptr;
+    int64_t n_virtual = 0;
+};
+
+static CountsView sg_view(const vb_counts* m, int64_t g_lo, int64_t g_hi, int fixed, const SegBuildOpts& opt) {
     CountsView v;
     v.C = m->C; v.V = m->V; v.N = m->N;
     v.g_lo = g_lo; v.g_hi = g_hi;
+    v.fixed = fixed; v.o_split = opt.o_split; v.v_owner = opt.v_owner; v.v_part = opt.v_part;
     v.cell_ptr = m->cell_ptr; v.cell_idx = m->cell_idx; v.cell_cnt = m->cell_cnt; v.cell_dp = m->cell_dp;
     v.snp_ptr = m->snp_ptr; v.snp_idx = m->snp_idx; v.snp_cnt = m->snp_cnt; v.snp_dp = m->snp_dp;
     return v;
@@ -304,12 +309,13 @@ static void seg_window(int prec, int* win_rows, int* nb, int* span) {
     if (*span < 1) *span = 1;
 }
 
-// g_lo / g_hi: the table rows this format covers (all of them: 0 / -1); max_grid: CTAs the launch may use (0: every SM)
 template <int ORI>
-static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st, int64_t g_lo = 0, int64_t g_hi = -1, int max_grid = 0) {
+static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st, const SegBuildOpts& opt = SegBuildOpts()) {
     memset(&g, 0, sizeof(g));
+    const int max_grid = opt.max_grid;
+    int64_t g_lo = opt.g_lo, g_hi = opt.g_hi;
     const int sm = max_grid > 0 ? max_grid : m->sm_count;
-    const int64_t O = ORI == 0 ? m->C : 2 * m->V;
+    const int64_t O = opt.v_owner ? opt.n_virtual : (ORI == 0 ? m->C : 2 * m->V);
     const int64_t G_all = ORI == 0 ? 2 * m->V : m->C;
     if (g_hi < 0 || g_hi > G_all) g_hi = G_all;
     const int64_t Gn = g_hi - g_lo;
@@ -321,7 +327,7 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st, int
     int n_win = (int)((Gn + win_rows - 1) / win_rows);
     if (n_win < 1) n_win = 1;
     const int64_t n_task = (O + VB_SEG_OWNERS - 1) / VB_SEG_OWNERS;
-    const CountsView v = sg_view(m, g_lo, g_hi);
+    const CountsView v = sg_view(m, g_lo, g_hi, fixed, opt);
     GsScratch tmp;
     int rc;
     uint32_t *nl, *nh, *rd, *nl_sorted;
@@ -361,7 +367,8 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st, int
         double total = 0.0;
         for (int64_t r = 0; r < O; ++r) total += hlen[r];
         int64_t first_sparse = O, moved = 0;
-        const int64_t budget = max_grid > 0 ? 0 : (int64_t)(total / 50.0);      // formats of the row-split pass keep every owner in the stream
+        // formats of the row-split pass and of virtual owners keep every owner in the stream
+        const int64_t budget = (max_grid > 0 || opt.v_owner) ? 0 : (int64_t)(total / 50.0);
         while (first_sparse > 0 && hlen[first_sparse - 1] <= VB_SPARSE_LEN && moved + hlen[first_sparse - 1] <= budget) {
             moved += hlen[first_sparse - 1];
             --first_sparse;
@@ -466,13 +473,101 @@ static int seg_build_one(vb_counts* m, SegSet& g, int prec, cudaStream_t st, int
     return VB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// rows far heavier than the rest
+// ---------------------------------------------------------------------------------------------
+// parts per owner: ceil(stream pairs / cap), at most 255; extra[o] = parts - 1 virtual owners
+__global__ void k_sg_parts(const uint32_t* __restrict__ n_light, int64_t n_owner, uint32_t cap, uint8_t* __restrict__ parts,
+                           uint32_t* __restrict__ extra) {
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n_owner; o += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t s = (n_light[o] + cap - 1) / cap;
+        s = s < 1u ? 1u : (s > 255u ? 255u : s);
+        parts[o] = (uint8_t)s;
+        extra[o] = s - 1u;
+    }
+}
+__global__ void k_sg_virtual(const uint8_t* __restrict__ parts, const int64_t* __restrict__ v_off, int64_t n_owner,
+                             int32_t* __restrict__ v_owner, uint8_t* __restrict__ v_part) {
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n_owner; o += (int64_t)gridDim.x * blockDim.x)
+        for (uint32_t j = 1; j < parts[o]; ++j) { v_owner[v_off[o] + j - 1] = (int32_t)o; v_part[v_off[o] + j - 1] = (uint8_t)j; }
+}
+
+// One orientation of one table kind.  When some owner carries more than VB_SEG_SKEW x the mean number of stream pairs
+// (a task is as long as its longest owner, so that owner's warp would be the critical path of the pass), the owners
+// above twice the mean are cut into parts: part 0 stays in this format, the others become virtual owners of g.excess.
+#define VB_SEG_SKEW 4
+template <int ORI>
+static int seg_build_fmt(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
+    int rc = seg_build_one<ORI>(m, g, prec, st);
+    static const int on = env_int("VIREO_B200_SEG_OWNER_SPLIT", 1);
+    if (rc || !on || prec == 1 || g.n_owner < 1 || g.n_light < 1) return rc;
+    const double mean = (double)g.n_light / (double)g.n_owner;
+    if ((double)g.max_len <= VB_SEG_SKEW * mean || g.max_len <= 256) return VB_OK;
+    const int64_t O = g.n_owner;
+    const int sm = m->sm_count;
+    const uint32_t cap = (uint32_t)(2.0 * mean) > 128u ? (uint32_t)(2.0 * mean) : 128u;
+    GsScratch tmp;
+    uint32_t *nl, *nh, *rd, *extra;
+    unsigned int* flags;
+    int64_t *ew, *v_off;
+    uint8_t* parts = nullptr;
+    int32_t* v_owner = nullptr;
+    uint8_t* v_part = nullptr;
+    if ((rc = tmp.alloc(&nl, O)) || (rc = tmp.alloc(&nh, O)) || (rc = tmp.alloc(&rd, O)) || (rc = tmp.alloc(&extra, O + 1)) ||
+        (rc = tmp.alloc(&flags, 4)) || (rc = tmp.alloc(&ew, O + 1)) || (rc = tmp.alloc(&v_off, O + 1)))
+        return rc;
+    const CountsView v = sg_view(m, 0, ORI == 0 ? 2 * m->V : m->C, 0, SegBuildOpts());
+    VB_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(unsigned int), st));
+    if (m->wide) k_sg_count<ORI, true><<<grid1d(O, sm), 256, 0, st>>>(v, O, 0, nl, nh, rd, flags);
+    else k_sg_count<ORI, false><<<grid1d(O, sm), 256, 0, st>>>(v, O, 0, nl, nh, rd, flags);
+    VB_CUDA(cudaGetLastError());
+    VB_CUDA(cudaMalloc(&parts, O));
+    k_sg_parts<<<grid1d(O, sm), 256, 0, st>>>(nl, O, cap, parts, extra);
+    k_sg_widen<<<grid1d(O + 1, sm), 256, 0, st>>>(extra, O, ew);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, ew, v_off, O + 1, st);
+    void* cub_tmp;
+    if ((rc = tmp.alloc((unsigned char**)&cub_tmp, tb))) { cudaFree(parts); return rc; }
+    cub::DeviceScan::ExclusiveSum(cub_tmp, tb, ew, v_off, O + 1, st);
+    int64_t n_virtual = 0;
+    VB_CUDA(cudaMemcpyAsync(&n_virtual, v_off + O, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VB_CUDA(cudaStreamSynchronize(st));
+    if (n_virtual < 1 || n_virtual >= (1ll << 31) - 64) { cudaFree(parts); return VB_OK; }
+    if (cudaMalloc(&v_owner, n_virtual * sizeof(int32_t)) != cudaSuccess || cudaMalloc(&v_part, n_virtual) != cudaSuccess) {
+        cudaFree(parts); cudaFree(v_owner); cudaGetLastError();
+        return VB_OK;                                   // the unsplit format stays
+    }
+    k_sg_virtual<<<grid1d(O, sm), 256, 0, st>>>(parts, v_off, O, v_owner, v_part);
+    VB_CUDA(cudaGetLastError());
+    // part 0 of every owner in this format, the other parts as owners of the excess format
+    SegSet main_set, *ex = new SegSet;
+    SegBuildOpts om, oe;
+    om.o_split = parts;
+    oe.o_split = parts; oe.v_owner = v_owner; oe.v_part = v_part; oe.n_virtual = n_virtual;
+    rc = seg_build_one<ORI>(m, main_set, prec, st, om);
+    if (!rc) rc = seg_build_one<ORI>(m, *ex, prec, st, oe);
+    if (!rc && (ex->n_heavy > 0 || ex->n_light < 1)) rc = VB_E_UNSUPPORTED;      // virtual owners stream every pair they have
+    if (rc) {                                                                    // keep the unsplit format
+        seg_set_free(main_set); seg_set_free(*ex); delete ex;
+        cudaFree(parts); cudaFree(v_owner); cudaFree(v_part);
+        cudaGetLastError();
+        return VB_OK;
+    }
+    seg_set_free(g);
+    g = main_set;
+    g.o_split = parts; g.n_virtual = n_virtual; g.v_owner = v_owner; g.v_part = v_part; g.excess = ex;
+    g.n_light += ex->n_light;                           // stream pairs of the pass, for the selector's residual rule
+    g.bytes += ex->bytes + O + n_virtual * 5;
+    return VB_OK;
+}
+
 int vb_seg_build(vb_counts* m, int prec, cudaStream_t st) {
     if (prec < 0 || prec > 2) { vb_set_error("bad table kind"); return VB_E_ARG; }
     if (m->sA[prec].built && m->sB[prec].built) return VB_OK;
     if (m->seg_failed[prec]) return VB_E_UNSUPPORTED;
     DeviceGuard dg(m->device);
-    int rc = seg_build_one<0>(m, m->sA[prec], prec, st);
-    if (!rc) rc = seg_build_one<1>(m, m->sB[prec], prec, st);
+    int rc = seg_build_fmt<0>(m, m->sA[prec], prec, st);
+    if (!rc) rc = seg_build_fmt<1>(m, m->sB[prec], prec, st);
     if (rc) {
         seg_set_free(m->sA[prec]);
         seg_set_free(m->sB[prec]);
@@ -563,12 +658,41 @@ extern "C" int vb_seg_verify(vb_counts* m, int prec, int ori, int64_t* out) {
     }
     for (int64_t o = 0; o < g.n_owner; ++o)
         for (int64_t q = hptr[o]; q < hptr[o + 1]; ++q) got.push_back(SegPair{(int32_t)o, hrow[q], hcnt[q]});
+    if (g.excess) {      // split owners: the records of the virtual owners belong to their real owners
+        const SegSet& e = *g.excess;
+        std::vector<int64_t> etoff;
+        std::vector<int32_t> eperm, vown;
+        std::vector<uint32_t> erec;
+        if ((rc = seg_download(etoff, e.task_off, (size_t)e.n_task_stream + 1)) || (rc = seg_download(eperm, e.perm, (size_t)e.n_task * VB_SEG_OWNERS)) ||
+            (rc = seg_download(erec, e.rec, (size_t)e.n_step * VB_SEG_OWNERS)) || (rc = seg_download(vown, g.v_owner, (size_t)g.n_virtual)))
+            return rc;
+        if (e.n_heavy) ++errors;
+        for (int64_t t = 0; t < e.n_task_stream; ++t) {
+            int64_t s = 0;
+            for (int64_t u = etoff[t]; u < etoff[t + 1]; ++u) {
+                const uint32_t* ss = &erec[(size_t)u * VB_SEG_OWNERS];
+                s += ss[0] >> 28;
+                if (s >= e.n_win) { ++errors; break; }
+                for (int sl = 0; sl < VB_SEG_OWNERS; ++sl) {
+                    const uint32_t w = ss[sl] & 0x0fffffffu;
+                    if ((w & 0xffffu) == 0) { ++nulls; continue; }
+                    const int64_t rr = w >> 16, lo = s * e.win_rows, hi = std::min<int64_t>((s + e.span) * (int64_t)e.win_rows, e.n_gather);
+                    int64_t r = lo - lo % ring_rows + rr;
+                    if (r < lo) r += ring_rows;
+                    const int32_t vo = eperm[(size_t)t * VB_SEG_OWNERS + sl];
+                    if (r >= hi || vo < 0 || vo >= g.n_virtual) { ++errors; continue; }
+                    got.push_back(SegPair{vown[vo], (int32_t)r, seg_code_count(w & 0xffffu, e.fixed)});
+                }
+            }
+        }
+        out[2] = g.n_step + e.n_step;
+    }
     std::sort(truth.begin(), truth.end());
     std::sort(got.begin(), got.end());
     if (truth.size() != got.size()) errors += (int64_t)(truth.size() > got.size() ? truth.size() - got.size() : got.size() - truth.size());
     for (size_t i = 0; i < truth.size() && i < got.size(); ++i)
         if (!(truth[i] == got[i])) ++errors;
-    out[0] = (int64_t)truth.size(); out[1] = errors; out[2] = g.n_step; out[3] = nulls;
+    out[0] = (int64_t)truth.size(); out[1] = errors; if (!g.excess) out[2] = g.n_step; out[3] = nulls;
     return VB_OK;
 }
 
@@ -1266,7 +1390,9 @@ int vb_seg_build_split(vb_counts* m, int prec, cudaStream_t st) {
     int rc = VB_OK;
     for (int r = 0; r <= R; ++r) sp.row_lo[r] = std::min<int64_t>((int64_t)r * wpr * win_rows, 2 * m->V);
     for (int r = 0; r < R && !rc; ++r) {
-        rc = seg_build_one<0>(m, sp.set[r], prec, st, sp.row_lo[r], sp.row_lo[r + 1], m->sm_count / R);
+        SegBuildOpts ro;
+        ro.g_lo = sp.row_lo[r]; ro.g_hi = sp.row_lo[r + 1]; ro.max_grid = m->sm_count / R;
+        rc = seg_build_one<0>(m, sp.set[r], prec, st, ro);
         if (!rc && sp.set[r].n_heavy > 0) { vb_set_error("row-split cell pass: residual pairs"); rc = VB_E_UNSUPPORTED; }   // the partial sums use the residual workspace
     }
     for (int r = 0; r < R && !rc; ++r) {
@@ -1305,6 +1431,28 @@ int vb_seg_launch_cell_split(const vb_counts* m, const EmP& p, int mode, cudaStr
     return VB_OK;
 }
 
+// split owners: the plain sums of an owner's virtual parts (format `excess`) are added to its residual sums H[o], which
+// the epilogue of the owner's own format adds to its accumulators.  One thread per (first virtual part, column); the
+// parts of an owner are consecutive, so the order of the additions is fixed.
+__global__ void __launch_bounds__(VB_THREADS)
+k_seg_fold(int64_t n_virtual, const int32_t* __restrict__ v_owner, const uint8_t* __restrict__ v_part, const uint8_t* __restrict__ o_split,
+           const double* __restrict__ vsum, double* __restrict__ H, int64_t n_owner, int RW, const int* __restrict__ ctrl) {
+    const int b = blockIdx.y;
+    if (ctrl && ctrl[b * VB_CTRL_N]) return;
+    const int64_t n = n_virtual * RW;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = e / RW;
+        const int c = (int)(e % RW);
+        if (v_part[v] != 1) continue;
+        const int64_t o = v_owner[v];
+        const int extra = (int)o_split[o] - 1;
+        double* h = H + ((size_t)b * n_owner + o) * RW + c;
+        double t = *h;
+        for (int j = 0; j < extra; ++j) t += vsum[((size_t)b * n_virtual + v + j) * RW + c];
+        *h = t;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: dispatch
 // ---------------------------------------------------------------------------------------------
@@ -1334,11 +1482,27 @@ static size_t g_seg_static[64] = {0};         // largest static shared memory of
 #define VB_SMEM_OPTIN ((size_t)227 * 1024)
 
 // ori 0: cell pass (table = p.Wt / p.Wq), ori 1: SNP pass (table = p.RP / p.RPq)
-// mode GM_PLAIN (ori 0, FP64 tables): `plain` says where the sums of this column chunk go
+// mode GM_PLAIN (FP64 tables): `plain` says where the plain sums go (a column chunk of the doublet pass, a row range
+// of the row-split cell pass, the virtual owners of a format with split owners)
 int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta_mode, const SegPlain* plain, cudaStream_t st) {
     const int prec = p.tiled == 3 ? 1 : (p.RW == 8 ? 2 : 0);
     const SegSet& g = (plain && plain->set) ? *plain->set : (ori ? m->sB[prec] : m->sA[prec]);
     if (!g.built) { vb_set_error("segment format was not built"); return VB_E_ARG; }
+    // split owners: the virtual parts first (plain sums of the excess format), folded into H below
+    const bool has_excess = g.excess != nullptr && prec != 1;
+    if (has_excess) {
+        SegSet& gm = const_cast<SegSet&>(g);
+        const int64_t need = (int64_t)p.B * g.n_virtual * p.RW;
+        if (gm.vsum_elems < need) {
+            cudaFree(gm.vsum); gm.vsum = nullptr; gm.vsum_elems = 0;
+            VB_CUDA(cudaMalloc(&gm.vsum, (size_t)need * sizeof(double)));
+            gm.vsum_elems = need;
+        }
+        SegPlain pe;
+        pe.out = g.vsum; pe.ld = p.RW; pe.off = 0; pe.cols = p.RW; pe.set = g.excess; pe.row0 = 0;
+        const int rc_e = vb_seg_launch(m, p, ori, GM_PLAIN, 0, &pe, st);
+        if (rc_e) return rc_e;
+    }
     const int dev_slot = m->device >= 0 && m->device < 64 ? m->device : 0;
     if (!g_seg_attr_set[dev_slot]) {
         // the opt-in limit covers static + dynamic shared memory: the fused tails (vb_tail.cuh) keep a few hundred
@@ -1375,11 +1539,11 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
         sa.table_stride = rows_all * (prec == 0 ? 128 : 64);
     }
     else { sa.table = reinterpret_cast<const unsigned char*>(ori ? p.RPq : p.Wq); sa.table_stride = rows_all * 64; }
-    sa.has_heavy = g.n_heavy > 0;
+    sa.has_heavy = g.n_heavy > 0 || has_excess;
     if (mode == GM_PLAIN) {
-        if (!plain || prec == 1 || ori != 0) { vb_set_error("plain segment pass: bad arguments"); return VB_E_ARG; }
+        if (!plain || prec == 1) { vb_set_error("plain segment pass: bad arguments"); return VB_E_ARG; }
         sa.plain_out = plain->out; sa.plain_ld = plain->ld; sa.plain_off = plain->off; sa.plain_cols = plain->cols;
-        sa.plain_stride = plain->set ? (int64_t)p.C * plain->ld : 0;      // row-split cell pass: one block of sums per restart
+        sa.plain_stride = plain->set ? g.n_owner * plain->ld : 0;         // a format of its own: one block of sums per restart
     }
     int grid_x;
     vb_seg_geometry(g, &grid_x, &sa.nwarps);
@@ -1391,6 +1555,13 @@ int vb_seg_launch(const vb_counts* m, const EmP& p, int ori, int mode, int theta
         VB_LAUNCH(cls, st, k_seg_heavy<<<dim3((unsigned)hb, p.B), VB_THREADS, 0, st>>>(
             g.n_owner, g.hptr, g.hrow, g.hcnt, tab64, g.n_gather * p.RW, p.RW, p.H, g.n_owner * p.RW, p.ctrl));
         VB_CUDA(cudaGetLastError());
+        if (has_excess) {
+            int64_t fb = (g.n_virtual * p.RW + VB_THREADS - 1) / VB_THREADS;
+            if (fb > (int64_t)m->sm_count * 8) fb = (int64_t)m->sm_count * 8;
+            VB_LAUNCH(cls, st, k_seg_fold<<<dim3((unsigned)fb, p.B), VB_THREADS, 0, st>>>(
+                g.n_virtual, g.v_owner, g.v_part, g.o_split, g.vsum, p.H, g.n_owner, p.RW, p.ctrl));
+            VB_CUDA(cudaGetLastError());
+        }
     }
     const dim3 grid(grid_x, p.B);
     const int threads = (sa.nwarps + 1) * 32;

@@ -186,6 +186,11 @@ extern "C" int64_t vb_counts_info(const vb_counts* m, int what) {
         case 8: return m->grid_elem;
         case 60: return m->auto_fallback;
         case 61: return m->rA[0].R > m->rA[2].R ? m->rA[0].R : m->rA[2].R;      // launches of the row-split cell pass (0: not in use)
+        case 63: {   // virtual owners of the built segment formats (rows cut into parts because they were far heavier than the rest)
+            int64_t n = 0;
+            for (int q = 0; q < 3; ++q) n += m->sA[q].n_virtual + m->sB[q].n_virtual;
+            return n;
+        }
         case 62: {   // worst row imbalance of the built segment formats, per mille: 1000 * longest owner / mean owner
             int64_t worst = 0;
             for (int q = 0; q < 3; ++q)

@@ -14,13 +14,37 @@ __device__ __forceinline__ void counts_at(const uint32_t* __restrict__ cnt, cons
     else { const uint32_t c = cnt[q]; a = c & 0xffffu; d = c >> 16; }
 }
 
+// FP64 tables: a count rides in a record when 2 * count is exact in a double cut to 4 mantissa bits, i.e. when it has
+// at most 5 significant bits (1..31, 32, 34, ..., 62, 64, 68, ...); fixed-point tables: counts up to 31.
+__host__ __device__ inline bool seg_count_ok(uint32_t c, int fixed) {
+    if (fixed) return c <= 31u;
+    if (c >= (1u << 24)) return false;
+    uint32_t t = c;
+    while (t >= 32u) { if (t & 1u) return false; t >>= 1; }
+    return true;
+}
+
 // ORI 0: owner = cell j, gather row = 2*snp + allele;  ORI 1: owner = 2*snp + allele, gather row = cell.
 // Calls f(gather_row - m.g_lo, count) for every pair with count > 0 and a gather row in [m.g_lo, m.g_hi), in ascending
 // gather-row order; returns false if a count pair with ad > dp was met (the formats do not represent it).
+// Split owners (m.o_split): of the pairs whose count rides in the stream, the k-th goes to part k % parts; `o` names
+// part 0 of a real owner, or -- with m.v_owner -- a virtual owner (real owner m.v_owner[o], part m.v_part[o]).  Pairs
+// for the residual list stay with part 0.
 template <int ORI, bool WIDE, typename F>
 __device__ __forceinline__ bool for_records(const CountsView& m, int64_t o, F&& f) {
     bool ok = true;
     const int64_t lo = m.g_lo, hi = m.g_hi;
+    uint32_t parts = 1, part = 0, k = 0;
+    if (m.v_owner) { part = m.v_part[o]; o = m.v_owner[o]; parts = m.o_split[o]; }
+    else if (m.o_split) parts = m.o_split[o];
+    auto emit = [&](int64_t g, uint32_t c) {
+        if (g < lo || g >= hi) return;
+        if (parts > 1) {
+            if (seg_count_ok(c, m.fixed)) { const bool mine = (k % parts) == part; ++k; if (!mine) return; }
+            else if (part != 0) return;
+        }
+        f((int)(g - lo), c);
+    };
     if (ORI == 0) {
         const int64_t p0 = m.cell_ptr[o], p1 = m.cell_ptr[o + 1];
         for (int64_t q = p0; q < p1; ++q) {
@@ -28,8 +52,8 @@ __device__ __forceinline__ bool for_records(const CountsView& m, int64_t o, F&& 
             counts_at<WIDE>(m.cell_cnt, m.cell_dp, q, a, d);
             if (a > d) { ok = false; continue; }
             const int64_t g = 2 * (int64_t)m.cell_idx[q];
-            if (d - a && g >= lo && g < hi) f((int)(g - lo), d - a);
-            if (a && g + 1 >= lo && g + 1 < hi) f((int)(g + 1 - lo), a);
+            if (d - a) emit(g, d - a);
+            if (a) emit(g + 1, a);
         }
     } else {
         const int64_t i = o >> 1;
@@ -40,8 +64,7 @@ __device__ __forceinline__ bool for_records(const CountsView& m, int64_t o, F&& 
             counts_at<WIDE>(m.snp_cnt, m.snp_dp, q, a, d);
             if (a > d) { ok = false; continue; }
             const uint32_t c = al ? a : d - a;
-            const int64_t g = m.snp_idx[q];
-            if (c && g >= lo && g < hi) f((int)(g - lo), c);
+            if (c) emit(m.snp_idx[q], c);
         }
     }
     return ok;
