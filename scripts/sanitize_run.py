@@ -42,6 +42,20 @@ C, V = (600, 500) if small else (1500, 1200)
 AD, DP = synth(C, V, 16, 0.06, 2)
 AD4, DP4 = synth(C, V // 2, 4, 0.06, 3)
 ADs, DPs = synth(200, 12500, 16, 0.05, 5)        # few cells, long table: the row-split cell pass of the segment family
+
+
+def synth_heavy(C, V, K, seed):
+    """power-law SNP coverage: rows far heavier than the mean, which the segment family cuts into parts"""
+    rng = np.random.default_rng(seed)
+    pv = np.minimum(1.0, 12.0 / (1 + np.arange(V)) ** 0.9)
+    mask = rng.random((V, C)) < pv[:, None]
+    dp = np.where(mask, rng.integers(1, 4, size=(V, C)), 0)
+    donor = rng.integers(0, K, C)
+    gt = rng.integers(0, 3, size=(V, K))
+    return csc_matrix(rng.binomial(dp, np.array([0.01, 0.5, 0.99])[gt[:, donor]])), csc_matrix(dp)
+
+
+ADh, DPh = synth_heavy(700, 900, 16, 7)
 for path in paths:
     _lib.set_path(path)
     np.random.seed(1)
@@ -59,6 +73,11 @@ for path in paths:
     print("%-5s ELBO %.10f  digest fit %s doublet %s sharded %s k4 %s bmm %s" % (
         path, m.ELBO_[-1], digest(m.ELBO_, m.ID_prob, m.GT_prob), digest(dbl, sgl, llr),
         digest(s.ELBO_, s.ID_prob), digest(m4.ELBO_, m4.ID_prob), digest(b.ELBO_iters, b.ID_prob)))
+    np.random.seed(4)
+    mh = vb.Vireo(n_cell=700, n_var=900, n_donor=16)
+    mh.fit(ADh, DPh, max_iter=3, min_iter=3, delay_fit_theta=1, verbose=False)
+    print("%-5s heavy rows: parts %d digest %s" % (path, int(_lib.load().vb_counts_info(vb.stage(ADh, DPh).handle, 63)),
+                                                    digest(mh.ELBO_, mh.ID_prob, mh.GT_prob)))
     if os.environ.get("VIREO_B200_SAN_NOSPLIT") != "1":      # the long-table case (window buffers are refilled)
         np.random.seed(3)
         ms = vb.Vireo(n_cell=200, n_var=12500, n_donor=16)
