@@ -502,10 +502,12 @@ static int seg_build_fmt(vb_counts* m, SegSet& g, int prec, cudaStream_t st) {
     static const int on = env_int("VIREO_B200_SEG_OWNER_SPLIT", 1);
     if (rc || !on || prec == 1 || g.n_owner < 1 || g.n_light < 1) return rc;
     const double mean = (double)g.n_light / (double)g.n_owner;
-    if ((double)g.max_len <= VB_SEG_SKEW * mean || g.max_len <= 256) return VB_OK;
+    static const double skew = getenv("VIREO_B200_SEG_SKEW") ? atof(getenv("VIREO_B200_SEG_SKEW")) : (double)VB_SEG_SKEW;
+    static const double capf = getenv("VIREO_B200_SEG_CAP") ? atof(getenv("VIREO_B200_SEG_CAP")) : 2.0;
+    if ((double)g.max_len <= skew * mean || g.max_len <= 256) return VB_OK;
     const int64_t O = g.n_owner;
     const int sm = m->sm_count;
-    const uint32_t cap = (uint32_t)(2.0 * mean) > 128u ? (uint32_t)(2.0 * mean) : 128u;
+    const uint32_t cap = (uint32_t)(capf * mean) > 128u ? (uint32_t)(capf * mean) : 128u;
     GsScratch tmp;
     uint32_t *nl, *nh, *rd, *extra;
     unsigned int* flags;
